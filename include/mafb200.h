@@ -1,0 +1,161 @@
+/*
+ * mafb200.h -- C ABI of the B200-native ConditionalMAF hot path.
+ *
+ * This is the drop-in boundary for jaxili's data-parallel hot path.  The reference
+ * (sachaguer/jaxili) has no FFI seam of its own (it is pure Python on JAX); the entry
+ * points below are what an XLA-FFI / ctypes binding for that path binds, one per
+ * reference call site (paths relative to the jaxili repository root):
+ *
+ *   mafb200_log_prob          <- model.apply(..., method="log_prob")
+ *                                jaxili/model.py:1073-1098 -> 903-921 -> 848-874 -> 718-743
+ *                                (callers: jaxili/loss.py:57,83,
+ *                                 jaxili/posterior/direct_posterior.py:106,
+ *                                 jaxili/train.py:337-340 eval_step)
+ *   mafb200_loss_grad         <- jax.value_and_grad(loss_nll_npe / loss_nll_nle)
+ *                                jaxili/train.py:330-332, jaxili/loss.py:35-83
+ *   mafb200_clip_adam         <- state.apply_gradients(grads) with the optax chain built in
+ *                                jaxili/train.py:246-300 (clip_by_global_norm -> adam(warmup_cosine))
+ *   mafb200_sample_from_noise <- model.apply(..., method="sample") with the base noise given
+ *   mafb200_sample_philox        jaxili/model.py:1116-1126 -> 923-947 -> 876-901 -> 745-773
+ *                                (caller: jaxili/posterior/direct_posterior.py:70-72)
+ *   mafb200_create            <- ConditionalMAF.setup / ConditionalMADE._create_masks
+ *                                jaxili/model.py:829-846, 581-663 (degrees in, masks derived)
+ *                                + NDE_w_Standardization constants, jaxili/inference/npe.py:383-399
+ *
+ * Conventions
+ *   - plain C types only; every device pointer is a caller-owned CUDA device pointer to
+ *     FP32 row-major data, 16-byte aligned; the library owns only the opaque handle and
+ *     its private scratch.  Nothing allocates on the hot path.
+ *   - every compute entry enqueues on the caller's stream (a cudaStream_t passed as
+ *     void*) and returns without synchronising; all are CUDA-graph capturable.
+ *   - return value 0 = ok, non-zero = error; the message is in mafb200_last_error()
+ *     (thread-local).  There is no CPU fallback: without a CUDA device every compute
+ *     entry fails.
+ *   - flat parameter order: for MAF layer k = 0..L-1, for masked linear i: kernel_i
+ *     (in_i x out_i, row-major, flax Dense convention) then bias_i (out_i).
+ */
+#ifndef MAFB200_H_
+#define MAFB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAFB200_MAX_HIDDEN 5
+
+/* activation enum: names follow jax.nn (jaxili/inventory/func_dict.py:28-31) */
+enum {
+  MAFB200_ACT_RELU = 0,
+  MAFB200_ACT_SILU = 1,
+  MAFB200_ACT_TANH = 2,
+  MAFB200_ACT_GELU = 3, /* jax.nn.gelu default: tanh approximation */
+  MAFB200_ACT_ELU = 4,
+  MAFB200_ACT_SIGMOID = 5,
+  MAFB200_ACT_SOFTPLUS = 6,
+  MAFB200_ACT_LEAKY_RELU = 7 /* negative_slope 0.01 */
+};
+
+/* flags for the compute entries */
+enum {
+  /* the handle's packed (mask-folded) weight image already reflects `params`:
+     skip the re-pack launch.  clip_adam leaves the image current. */
+  MAFB200_PACKED_CURRENT = 1,
+  /* clip_adam: the handle's squared-norm partials already describe `grad` (true right
+     after loss_grad on the same handle when grad was not modified, e.g. no all-reduce):
+     skip the norm launch. */
+  MAFB200_NORM_CURRENT = 2
+};
+
+typedef struct mafb200_handle_s* mafb200_handle;
+
+/* ConditionalMAF(n_in, n_cond, n_layers, layers, activation, use_reverse)
+   jaxili/model.py:821-827 */
+typedef struct {
+  int32_t n_in;
+  int32_t n_cond;
+  int32_t n_layers;
+  int32_t n_hidden;                    /* len(layers) >= 1 */
+  int32_t hidden[MAFB200_MAX_HIDDEN];  /* layers */
+  int32_t activation;                  /* MAFB200_ACT_* */
+  int32_t use_reverse;
+} MafDesc;
+
+/* optimizer_hparams of TrainerModule.init_optimizer, jaxili/train.py:257-292 */
+typedef struct {
+  float lr;            /* peak learning rate */
+  float warmup;        /* warmup_steps (NPE.train passes 0.1) */
+  float decay_steps;   /* cosine horizon, same unit as warmup */
+  float init_factor;   /* init_value = init_factor*lr  (0.01) */
+  float end_factor;    /* end_value  = end_factor*lr   (0.01) */
+  float b1, b2, eps;   /* adam: 0.9, 0.999, 1e-8 */
+  float clip;          /* clip_by_global_norm max_norm (5.0) */
+  float weight_decay;  /* adamw only */
+  int32_t kind;        /* 0 adam, 1 sgd (+decayed weights), 2 adamw */
+} MafOptDesc;
+
+const char* mafb200_last_error(void);
+int mafb200_version(void);
+
+/* degrees: for each MAF layer k, the concatenated hidden degree vectors m^1..m^n
+   (sum(hidden) int32 each), exactly as np.random.randint produced them
+   (jaxili/model.py:613-616); masks are derived as in 621-657.
+   shift/scale/mean/std: host arrays (n_in, n_in, n_cond, n_cond) of the
+   ScalarAffine / Standardizer; NULL = identity. */
+int mafb200_create(const MafDesc* desc, const int32_t* degrees,
+                   const float* shift, const float* scale,
+                   const float* mean, const float* std,
+                   int device, mafb200_handle* out);
+int mafb200_destroy(mafb200_handle h);
+int mafb200_set_standardization(mafb200_handle h, const float* shift, const float* scale,
+                                const float* mean, const float* std);
+
+int64_t mafb200_param_count(mafb200_handle h);
+/* writes the 0/1 mask in flat parameter order (biases 1) to a host buffer of param_count bytes */
+int mafb200_get_mask(mafb200_handle h, uint8_t* mask_host);
+/* bytes of dynamic shared memory, rows per tile and CTAs the flow kernel will use (for reports) */
+int mafb200_query(mafb200_handle h, int32_t* smem_bytes, int32_t* tile_rows,
+                  int32_t* max_ctas, int32_t* stash_all);
+
+/* mask-fold + pad + transpose `params` into the handle's packed image */
+int mafb200_pack(mafb200_handle h, const float* params, void* stream);
+
+/* out_logp[b] = log p(x_b | y_b), b < B.  x: B x n_in, y: B x n_cond. */
+int mafb200_log_prob(mafb200_handle h, const float* params, const float* x, const float* y,
+                     int64_t B, float* out_logp, int32_t flags, void* stream);
+
+/* out_loss[0] = -inv_global_B * sum_b log p(x_b|y_b); out_grad = d out_loss / d params
+   (P floats, masked entries exactly 0).  If batch_index != NULL the batch is rows
+   [(batch_index[0] % n_batches) * B, +B) of x / y (device-side batch selection for
+   graph replay); otherwise rows [0, B). */
+int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, const float* y,
+                      int64_t B, float inv_global_B,
+                      const int32_t* batch_index, int64_t n_batches,
+                      float* out_loss, float* out_grad, int32_t flags, void* stream);
+
+/* optax.chain(clip_by_global_norm, adam(schedule)) + apply_gradients, in place on
+   params / m / v; step[0] (device int32) is the optax count and is incremented.
+   Leaves the packed image current. */
+int mafb200_clip_adam(mafb200_handle h, float* params, const float* grad, float* m, float* v,
+                      int32_t* step, const MafOptDesc* opt, int32_t flags, void* stream);
+
+/* theta[r] = scale * MAF^-1(u[r] | (y_obs[r / rows_per_obs] - mean)/std) + shift.
+   u, out: N x n_in; y_obs: n_obs x n_cond with N <= n_obs * rows_per_obs. */
+int mafb200_sample_from_noise(mafb200_handle h, const float* params, const float* u,
+                              const float* y_obs, int64_t n_obs, int64_t rows_per_obs,
+                              int64_t N, float* out, int32_t flags, void* stream);
+/* same with u ~ N(0,I) drawn in-kernel: Philox4x32-10, subsequence = row_offset + r */
+int mafb200_sample_philox(mafb200_handle h, const float* params, uint64_t seed,
+                          uint64_t row_offset, const float* y_obs, int64_t n_obs,
+                          int64_t rows_per_obs, int64_t N, float* out, int32_t flags,
+                          void* stream);
+
+/* FP32 FFMA micro-benchmark used as the roofline denominator (bench.py): runs `iters`
+   dependent-chain-free FFMA blocks on every SM, returns achieved TFLOP/s. */
+int mafb200_ffma_peak(int device, int32_t iters, float* out_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAFB200_H_ */

@@ -1,0 +1,618 @@
+// mafb200.cu -- C ABI (include/mafb200.h), planner and launchers of the B200-native MAF hot path.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include "../../include/mafb200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "flow_kernel.cuh"
+#include "opt_kernels.cuh"
+#include "sample_kernel.cuh"
+
+using namespace mafb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                             \
+  } while (0)
+
+constexpr int kSmemLimit = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100
+constexpr int kFlowThreads = 384;
+constexpr int kSampleWarps = 8;
+
+inline int r4(int v) { return (v + 3) & ~3; }
+
+}  // namespace
+
+struct mafb200_handle_s {
+  MafDesc desc{};
+  int device = 0, n_sm = 0;
+  Plan plan{};
+  SamplePlan splan{};
+  SamplePackArgs spack{};
+  int dims[MAFB_MAX_LIN + 1]{};
+  std::vector<uint8_t> mask_host;
+  // device buffers
+  uint8_t* mask = nullptr;
+  float* wimg = nullptr;
+  float* simg = nullptr;
+  int* spos = nullptr;
+  float* stdc = nullptr;        // [shift D][inv_scale D][mean C][std C][scale D]
+  float* partial = nullptr;     // [n_sm][P]
+  float* partial_loss = nullptr;
+  float* normpart = nullptr;
+  unsigned int* done_counter = nullptr;
+  float logdet_const = 0.f;
+  int n_norm = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------ masks from degrees
+// jaxili/model.py:621-657.  deg_h[l] = degrees of hidden level l+1; input degrees arange(D).
+void build_masks(const MafDesc& d, const int32_t* degrees, std::vector<uint8_t>& mask, const int* dims,
+                 int n_lin, int ppl) {
+  const int D = d.n_in, L = d.n_layers;
+  int hsum = 0;
+  for (int i = 0; i < d.n_hidden; ++i) hsum += d.hidden[i];
+  mask.assign((size_t)L * ppl, 1);
+  for (int k = 0; k < L; ++k) {
+    const int32_t* dk = degrees + (size_t)k * hsum;
+    std::vector<std::vector<int>> deg(n_lin + 1);
+    deg[0].resize(D);
+    for (int j = 0; j < D; ++j) deg[0][j] = j;
+    int off = 0;
+    for (int l = 1; l < n_lin; ++l) {
+      deg[l].assign(dk + off, dk + off + d.hidden[l - 1]);
+      off += d.hidden[l - 1];
+    }
+    deg[n_lin] = deg[0];
+    size_t p = (size_t)k * ppl;
+    for (int i = 0; i < n_lin; ++i) {
+      const int K = dims[i], N = dims[i + 1];
+      for (int a = 0; a < K; ++a)
+        for (int b = 0; b < N; ++b) {
+          uint8_t m;
+          if (i == n_lin - 1) m = deg[i][a] < deg[n_lin][b % D];          // strict, duplicated (mu|logp)
+          else if (i == 0) m = (a >= D) ? 1 : (deg[0][a] <= deg[1][b]);   // conditioning rows all ones
+          else m = deg[i][a] <= deg[i + 1][b];
+          mask[p + (size_t)a * N + b] = m;
+        }
+      p += (size_t)K * N + N;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ flow-kernel planner
+bool plan_layout(Plan& P, int R, bool stash_all, int n_wbuf) {
+  P.R = R;
+  P.RP = R + 4;
+  P.stash_all = stash_all ? 1 : 0;
+  P.n_wbuf = n_wbuf;
+  const int RP = P.RP;
+  int o = 0;
+  P.wbuf_stride = stash_all ? std::max(P.fwd_floats, P.bwd_floats) : P.img_floats;
+  P.o_wbuf = o;
+  o += n_wbuf * P.wbuf_stride;
+  P.stage_stride = r4(R * (P.D + P.C));
+  P.o_stage = o;
+  o += 2 * P.stage_stride;
+  P.xin_stride = r4(P.K0) * RP;
+  P.o_xin = o;
+  o += P.L * P.xin_stride;
+  int rows = 0, maxhp = 4;
+  for (int i = 1; i < P.n_lin; ++i) {
+    P.h_off[i] = rows * RP;
+    rows += P.lin[i].KP;
+    maxhp = std::max(maxhp, P.lin[i].KP);
+  }
+  for (int i = 1; i < P.n_lin; ++i) {
+    P.d_off[i] = P.need_d ? rows * RP : 0;
+    if (P.need_d) rows += P.lin[i].KP;
+  }
+  P.s_off = rows * RP;
+  rows += P.DP;
+  P.v_off = rows * RP;
+  rows += P.DP;
+  P.slot_stride = rows * RP;
+  P.o_slot = o;
+  o += (stash_all ? P.L : 1) * P.slot_stride;
+  P.o_obuf = o;
+  o += r4(2 * P.D) * RP;
+  P.o_gu = o;
+  o += P.DP * RP;
+  P.o_gx = o;
+  o += P.DP * RP;
+  P.o_ld = o;
+  o += P.DP * RP;
+  P.o_g[0] = o;
+  o += maxhp * RP;
+  P.o_g[1] = o;
+  o += maxhp * RP;
+  P.smem_bytes = 64 + o * 4;
+  return P.smem_bytes <= kSmemLimit;
+}
+
+bool make_plan(const MafDesc& d, const int* dims, Plan& P) {
+  std::memset(&P, 0, sizeof(P));
+  P.D = d.n_in;
+  P.C = d.n_cond;
+  P.K0 = d.n_in + d.n_cond;
+  P.L = d.n_layers;
+  P.n_lin = d.n_hidden + 1;
+  P.act = d.activation;
+  P.reverse = d.use_reverse ? 1 : 0;
+  P.DP = r4(P.D);
+  P.need_d = d.activation != MAFB200_ACT_RELU;
+  P.threads = kFlowThreads;
+  int fo = 0, bo = 0, po = 0;
+  for (int i = 0; i < P.n_lin; ++i) {
+    LinDesc& ln = P.lin[i];
+    ln.K = dims[i];
+    ln.N = dims[i + 1];
+    ln.KP = r4(ln.K);
+    ln.NP = r4(ln.N);
+    ln.w_off = fo;
+    fo += ln.K * ln.NP;
+    ln.b_off = fo;
+    fo += ln.NP;
+    ln.wt_off = bo;
+    bo += ln.N * ln.KP;
+    ln.pw_off = po;
+    po += ln.K * ln.N;
+    ln.pb_off = po;
+    po += ln.N;
+  }
+  P.fwd_floats = r4(fo);
+  P.bwd_floats = r4(bo);
+  P.img_floats = P.fwd_floats + P.bwd_floats;
+  P.ppl = po;
+  P.P = po * P.L;
+  static const int Rs[] = {32, 16, 8, 4};
+  for (int R : Rs)
+    for (int stash = 1; stash >= 0; --stash)
+      for (int nb = 2; nb >= 1; --nb)
+        if (plan_layout(P, R, stash != 0, nb)) return true;
+  return false;
+}
+
+// ------------------------------------------------------------------ sampler planner + sorted positions
+bool make_sample_plan(const MafDesc& d, const int* dims, SamplePlan& S) {
+  std::memset(&S, 0, sizeof(S));
+  S.D = d.n_in;
+  S.C = d.n_cond;
+  S.L = d.n_layers;
+  S.n_lin = d.n_hidden + 1;
+  S.act = d.activation;
+  S.reverse = d.use_reverse ? 1 : 0;
+  if (S.D > MAFB_MAX_DEG) return false;
+  S.width[0] = dims[0];
+  for (int l = 1; l < S.n_lin; ++l) S.width[l] = r4(dims[l] + S.D);
+  S.width[S.n_lin] = r4(2 * S.D);
+  int o = 0;
+  for (int i = 0; i < S.n_lin; ++i) {
+    S.w_off[i] = o;
+    o += S.width[i] * S.width[i + 1];
+    o = r4(o);
+    S.b_off[i] = o;
+    o += S.width[i + 1];
+    o = r4(o);
+  }
+  S.tab_off = o;
+  o += r4((S.n_lin - 1) * (S.D + 1));
+  S.img_floats = o;
+  S.rows_per_warp = 32;
+  S.RP = 36;
+  int w = 0;
+  for (int l = 1; l < S.n_lin; ++l) {
+    S.lvl_off[l] = w;
+    w += S.width[l] * S.RP;
+  }
+  S.y_off = w;
+  w += std::max(4, r4(S.C)) * S.RP;
+  S.u_off = w;
+  w += r4(S.D) * S.RP;
+  S.x_off = w;
+  w += r4(S.D) * S.RP;
+  S.warp_stride = w;
+  for (int n_img = 2; n_img >= 1; --n_img) {
+    S.n_img = n_img;
+    S.o_img = 0;
+    S.o_warp = n_img * S.img_floats;
+    S.warps = kSampleWarps;
+    S.smem_bytes = 64 + (S.o_warp + S.warps * S.warp_stride) * 4;
+    if (S.smem_bytes <= kSmemLimit) return true;
+  }
+  return false;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char* mafb200_last_error(void) { return g_err.c_str(); }
+int mafb200_version(void) { return 100; }
+
+int mafb200_set_standardization(mafb200_handle h, const float* shift, const float* scale,
+                                const float* mean, const float* stdv) {
+  if (!h) return fail("null handle");
+  const int D = h->desc.n_in, C = h->desc.n_cond;
+  std::vector<float> c(3 * D + 2 * C);
+  float ld = 0.f;
+  for (int j = 0; j < D; ++j) {
+    const float sh = shift ? shift[j] : 0.f, sc = scale ? scale[j] : 1.f;
+    c[j] = sh;
+    c[D + j] = 1.0f / sc;                 // distrax.ScalarAffine: inv_scale = 1/scale
+    c[2 * D + 2 * C + j] = sc;
+    ld += -logf(fabsf(sc));               // inverse_log_det_jacobian summed (model.py:1094-1095)
+  }
+  for (int j = 0; j < C; ++j) {
+    c[2 * D + j] = mean ? mean[j] : 0.f;
+    c[2 * D + C + j] = stdv ? stdv[j] : 1.f;
+  }
+  h->logdet_const = ld;
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpy(h->stdc, c.data(), c.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shift, const float* scale,
+                   const float* mean, const float* stdv, int device, mafb200_handle* out) {
+  if (!desc || !degrees || !out) return fail("mafb200_create: null argument");
+  const MafDesc& d = *desc;
+  if (d.n_in < 2) return fail("n_in must be >= 2 (jaxili's randint(0, n_in-1) needs it)");
+  if (d.n_cond < 0 || d.n_layers < 1) return fail("bad n_cond / n_layers");
+  if (d.n_hidden < 1 || d.n_hidden > MAFB200_MAX_HIDDEN) return fail("layers must have 1..5 entries");
+  if (d.activation < 0 || d.activation > MAFB200_ACT_LEAKY_RELU) return fail("unsupported activation");
+  for (int i = 0; i < d.n_hidden; ++i)
+    if (d.hidden[i] < 1) return fail("hidden sizes must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device: the MAF hot path has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail("bad device index");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail("this library is built for sm_100a (B200) only");
+
+  mafb200_handle h = new mafb200_handle_s();
+  h->desc = d;
+  h->device = device;
+  h->n_sm = prop.multiProcessorCount;
+  h->dims[0] = d.n_in + d.n_cond;
+  for (int i = 0; i < d.n_hidden; ++i) h->dims[i + 1] = d.hidden[i];
+  h->dims[d.n_hidden + 1] = 2 * d.n_in;
+  if (!make_plan(d, h->dims, h->plan)) {
+    delete h;
+    return fail("model too wide for the shared-memory-resident (narrow) path; wide tcgen05 path not built yet");
+  }
+  const bool have_sampler = make_sample_plan(d, h->dims, h->splan);
+  if (!have_sampler) h->splan.img_floats = 0;
+  const Plan& P = h->plan;
+  build_masks(d, degrees, h->mask_host, h->dims, P.n_lin, P.ppl);
+
+#define CUH(call)                                                           \
+  do {                                                                      \
+    cudaError_t e_ = (call);                                                \
+    if (e_ != cudaSuccess) {                                                \
+      mafb200_destroy(h);                                                   \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_));      \
+    }                                                                       \
+  } while (0)
+  CUH(cudaMalloc(&h->mask, P.P));
+  CUH(cudaMemcpy(h->mask, h->mask_host.data(), P.P, cudaMemcpyHostToDevice));
+  CUH(cudaMalloc(&h->wimg, (size_t)P.L * P.img_floats * 4));
+  CUH(cudaMemset(h->wimg, 0, (size_t)P.L * P.img_floats * 4));
+  CUH(cudaMalloc(&h->stdc, (3 * P.D + 2 * P.C) * 4));
+  CUH(cudaMalloc(&h->partial, (size_t)h->n_sm * P.P * 4));
+  CUH(cudaMalloc(&h->partial_loss, h->n_sm * 4));
+  h->n_norm = (P.P + RED_IDX - 1) / RED_IDX;
+  CUH(cudaMalloc(&h->normpart, h->n_norm * 4));
+  CUH(cudaMemset(h->normpart, 0, h->n_norm * 4));
+  CUH(cudaMalloc(&h->done_counter, 4));
+  CUH(cudaMemset(h->done_counter, 0, 4));
+
+  if (have_sampler) {
+    // degree-sorted positions and group tables
+    const SamplePlan& S = h->splan;
+    const int n_lin = S.n_lin, D = S.D;
+    int hsum = 0, tot = 0;
+    for (int i = 0; i < d.n_hidden; ++i) hsum += d.hidden[i];
+    for (int l = 0; l <= n_lin; ++l) {
+      h->spack.lvl_start[l] = tot;
+      tot += h->dims[l];
+    }
+    h->spack.spos_per_layer = tot;
+    std::vector<int> spos((size_t)P.L * tot);
+    std::vector<float> simg((size_t)P.L * S.img_floats, 0.f);
+    for (int k = 0; k < P.L; ++k) {
+      int* pos = spos.data() + (size_t)k * tot;
+      for (int a = 0; a < h->dims[0]; ++a) pos[a] = a;
+      const int32_t* dk = degrees + (size_t)k * hsum;
+      int off = 0;
+      int* tab = reinterpret_cast<int*>(simg.data() + (size_t)k * S.img_floats + S.tab_off);
+      for (int l = 1; l < n_lin; ++l) {
+        const int H = h->dims[l];
+        int* pl = pos + h->spack.lvl_start[l];
+        int* T = tab + (l - 1) * (D + 1);
+        int col = 0;
+        T[0] = 0;
+        for (int m = 0; m < D; ++m) {
+          for (int a = 0; a < H; ++a)
+            if (dk[off + a] == m) pl[a] = col++;
+          col = (col + SN_ - 1) / SN_ * SN_;
+          T[m + 1] = col;
+        }
+        if (col > S.width[l]) {
+          mafb200_destroy(h);
+          return fail("internal: sorted width overflow");
+        }
+        for (int a = 0; a < H; ++a)
+          if (dk[off + a] < 0 || dk[off + a] >= D) {
+            mafb200_destroy(h);
+            return fail("degree out of range");
+          }
+        off += H;
+      }
+      int* po = pos + h->spack.lvl_start[n_lin];
+      for (int n = 0; n < 2 * D; ++n) po[n] = n < D ? 2 * n : 2 * (n - D) + 1;
+    }
+    CUH(cudaMalloc(&h->spos, spos.size() * sizeof(int)));
+    CUH(cudaMemcpy(h->spos, spos.data(), spos.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUH(cudaMalloc(&h->simg, simg.size() * 4));
+    CUH(cudaMemcpy(h->simg, simg.data(), simg.size() * 4, cudaMemcpyHostToDevice));
+  }
+
+  // opt in to the large dynamic shared memory carve-out for every kernel we may launch
+  const int sb = P.smem_bytes;
+  CUH(cudaFuncSetAttribute(maf_flow_kernel<true, true, kFlowThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+  CUH(cudaFuncSetAttribute(maf_flow_kernel<true, false, kFlowThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+  CUH(cudaFuncSetAttribute(maf_flow_kernel<false, true, kFlowThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+  CUH(cudaFuncSetAttribute(maf_flow_kernel<false, false, kFlowThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+  if (have_sampler) {
+    CUH(cudaFuncSetAttribute(maf_sample_kernel<true, kSampleWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->splan.smem_bytes));
+    CUH(cudaFuncSetAttribute(maf_sample_kernel<false, kSampleWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->splan.smem_bytes));
+  }
+#undef CUH
+  *out = h;
+  if (mafb200_set_standardization(h, shift, scale, mean, stdv)) {
+    mafb200_destroy(h);
+    *out = nullptr;
+    return 1;
+  }
+  return 0;
+}
+
+int mafb200_destroy(mafb200_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaFree(h->mask);
+  cudaFree(h->wimg);
+  cudaFree(h->simg);
+  cudaFree(h->spos);
+  cudaFree(h->stdc);
+  cudaFree(h->partial);
+  cudaFree(h->partial_loss);
+  cudaFree(h->normpart);
+  cudaFree(h->done_counter);
+  delete h;
+  return 0;
+}
+
+int64_t mafb200_param_count(mafb200_handle h) { return h ? h->plan.P : -1; }
+
+int mafb200_get_mask(mafb200_handle h, uint8_t* mask_host) {
+  if (!h || !mask_host) return fail("null argument");
+  std::memcpy(mask_host, h->mask_host.data(), h->mask_host.size());
+  return 0;
+}
+
+int mafb200_query(mafb200_handle h, int32_t* smem_bytes, int32_t* tile_rows, int32_t* max_ctas,
+                  int32_t* stash_all) {
+  if (!h) return fail("null handle");
+  if (smem_bytes) *smem_bytes = h->plan.smem_bytes;
+  if (tile_rows) *tile_rows = h->plan.R;
+  if (max_ctas) *max_ctas = h->n_sm;
+  if (stash_all) *stash_all = h->plan.stash_all;
+  return 0;
+}
+
+int mafb200_pack(mafb200_handle h, const float* params, void* stream) {
+  if (!h || !params) return fail("null argument");
+  const Plan& P = h->plan;
+  pack_kernel<<<(P.P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, params, h->mask, h->wimg);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int launch_geometry(mafb200_handle h, int64_t B, int& Rt, int& n_tiles, int& grid) {
+  const int R = h->plan.R;
+  const int64_t rows_per_cta = (B + h->n_sm - 1) / h->n_sm;
+  const int64_t n_t = (rows_per_cta + R - 1) / R;
+  const int64_t rt = (rows_per_cta + n_t - 1) / n_t;
+  Rt = (int)std::min<int64_t>(R, (rt + 3) & ~3LL);
+  const int64_t T = (B + Rt - 1) / Rt;
+  if (T > 0x7fffffff) return fail("batch too large");
+  n_tiles = (int)T;
+  grid = (int)std::min<int64_t>(h->n_sm, T);
+  return 0;
+}
+
+int mafb200_log_prob(mafb200_handle h, const float* params, const float* x, const float* y, int64_t B,
+                     float* out_logp, int32_t flags, void* stream) {
+  if (!h || !params || !x || !out_logp || (h->desc.n_cond && !y)) return fail("null argument");
+  if (B <= 0) return B == 0 ? 0 : fail("negative batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!(flags & MAFB200_PACKED_CURRENT) && mafb200_pack(h, params, stream)) return 1;
+  FlowArgs A{};
+  A.wimg = h->wimg;
+  A.x = x;
+  A.y = y;
+  A.B = B;
+  A.batch_index = nullptr;
+  A.n_batches = 1;
+  A.stdc = h->stdc;
+  A.logdet_const = h->logdet_const;
+  A.inv_b = 1.f;
+  A.out_logp = out_logp;
+  int grid;
+  if (launch_geometry(h, B, A.Rt, A.n_tiles, grid)) return 1;
+  const Plan& P = h->plan;
+  if (P.act == MAFB200_ACT_RELU)
+    maf_flow_kernel<false, true, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
+  else
+    maf_flow_kernel<false, false, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, const float* y, int64_t B,
+                      float inv_global_B, const int32_t* batch_index, int64_t n_batches, float* out_loss,
+                      float* out_grad, int32_t flags, void* stream) {
+  if (!h || !params || !x || !out_loss || !out_grad || (h->desc.n_cond && !y)) return fail("null argument");
+  if (B <= 0) return fail("loss_grad needs a non-empty batch");
+  if (batch_index && n_batches <= 0) return fail("n_batches must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!(flags & MAFB200_PACKED_CURRENT) && mafb200_pack(h, params, stream)) return 1;
+  FlowArgs A{};
+  A.wimg = h->wimg;
+  A.x = x;
+  A.y = y;
+  A.B = B;
+  A.batch_index = batch_index;
+  A.n_batches = batch_index ? n_batches : 1;
+  A.stdc = h->stdc;
+  A.logdet_const = h->logdet_const;
+  A.inv_b = inv_global_B;
+  A.partial_grad = h->partial;
+  A.partial_loss = h->partial_loss;
+  int grid;
+  if (launch_geometry(h, B, A.Rt, A.n_tiles, grid)) return 1;
+  const Plan& P = h->plan;
+  if (P.act == MAFB200_ACT_RELU)
+    maf_flow_kernel<true, true, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
+  else
+    maf_flow_kernel<true, false, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
+  CU(cudaGetLastError());
+  reduce_kernel<<<h->n_norm, RED_IDX * RED_PARTS, 0, st>>>(h->partial, grid, P.P, h->mask, out_grad,
+                                                         h->partial_loss, out_loss, h->normpart);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int mafb200_clip_adam(mafb200_handle h, float* params, const float* grad, float* m, float* v, int32_t* step,
+                      const MafOptDesc* opt, int32_t flags, void* stream) {
+  if (!h || !params || !grad || !step || !opt) return fail("null argument");
+  if (opt->kind < 0 || opt->kind > 2) return fail("unknown optimizer kind");
+  if (opt->kind != 1 && (!m || !v)) return fail("adam needs m and v");
+  if (opt->decay_steps - opt->warmup <= 0.f) return fail("cosine_decay_schedule requires positive decay_steps");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Plan& P = h->plan;
+  if (!(flags & MAFB200_NORM_CURRENT)) {
+    sqnorm_kernel<<<h->n_norm, RED_IDX, 0, st>>>(grad, P.P, h->normpart);
+    CU(cudaGetLastError());
+  }
+  OptArgs O{opt->lr, opt->warmup, opt->decay_steps, opt->init_factor, opt->end_factor, opt->b1, opt->b2,
+            opt->eps, opt->clip, opt->weight_decay, opt->kind};
+  clip_adam_kernel<<<h->n_norm, RED_IDX, 0, st>>>(P, O, params, grad, m, v, step, h->normpart, h->n_norm,
+                                                  h->mask, h->wimg, h->done_counter, nullptr);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int sample_common(mafb200_handle h, const float* params, const float* u, uint64_t seed,
+                         uint64_t row_offset, const float* y_obs, int64_t n_obs, int64_t rows_per_obs,
+                         int64_t N, float* out, int32_t flags, void* stream) {
+  if (!h || !params || !out || (h->desc.n_cond && !y_obs)) return fail("null argument");
+  if (h->splan.img_floats == 0) return fail("sampler not available for this configuration");
+  if (N <= 0) return N == 0 ? 0 : fail("negative sample count");
+  if (n_obs <= 0 || rows_per_obs <= 0 || n_obs * rows_per_obs < N)
+    return fail("need n_obs * rows_per_obs >= N");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Plan& P = h->plan;
+  const SamplePlan& S = h->splan;
+  if (!(flags & MAFB200_PACKED_CURRENT)) {
+    pack_sample_kernel<<<(P.P + 255) / 256, 256, 0, st>>>(P, S, h->spack, params, h->mask, h->spos, h->simg);
+    CU(cudaGetLastError());
+  }
+  SampleArgs A{};
+  A.simg = h->simg;
+  A.u = u;
+  A.seed = seed;
+  A.row_offset = row_offset;
+  A.y_obs = y_obs;
+  A.n_obs = n_obs;
+  A.rows_per_obs = rows_per_obs;
+  A.N = N;
+  A.stdc = h->stdc;
+  A.out = out;
+  const int64_t tiles = (N + 31) / 32;
+  const int grid = (int)std::min<int64_t>(h->n_sm, (tiles + kSampleWarps - 1) / kSampleWarps);
+  if (S.act == MAFB200_ACT_RELU)
+    maf_sample_kernel<true, kSampleWarps><<<grid, kSampleWarps * 32, S.smem_bytes, st>>>(S, A);
+  else
+    maf_sample_kernel<false, kSampleWarps><<<grid, kSampleWarps * 32, S.smem_bytes, st>>>(S, A);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int mafb200_sample_from_noise(mafb200_handle h, const float* params, const float* u, const float* y_obs,
+                              int64_t n_obs, int64_t rows_per_obs, int64_t N, float* out, int32_t flags,
+                              void* stream) {
+  if (!u) return fail("null noise pointer");
+  return sample_common(h, params, u, 0, 0, y_obs, n_obs, rows_per_obs, N, out, flags, stream);
+}
+
+int mafb200_sample_philox(mafb200_handle h, const float* params, uint64_t seed, uint64_t row_offset,
+                          const float* y_obs, int64_t n_obs, int64_t rows_per_obs, int64_t N, float* out,
+                          int32_t flags, void* stream) {
+  return sample_common(h, params, nullptr, seed, row_offset, y_obs, n_obs, rows_per_obs, N, out, flags, stream);
+}
+
+int mafb200_ffma_peak(int device, int32_t iters, float* out_tflops) {
+  if (!out_tflops || iters <= 0) return fail("bad argument");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  float* buf = nullptr;
+  CU(cudaMalloc(&buf, (size_t)blocks * threads * 4));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  ffma_peak_kernel<<<blocks, threads>>>(buf, iters / 4 + 1, 1e-3f);   // warm-up
+  float best = 0.f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(e0));
+    ffma_peak_kernel<<<blocks, threads>>>(buf, iters, 1e-3f);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = (double)blocks * threads * (double)iters * 8 * 16 * 2;
+    best = std::max(best, (float)(flops / (ms * 1e-3) / 1e12));
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *out_tflops = best;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,230 @@
+// opt_kernels.cuh -- parameter packing, partial-gradient reduction, global-norm clip + Adam.
+//
+//   pack_kernel        mask-fold + pad + transpose the flat parameters into the per-layer
+//                      shared-memory images the flow kernel bulk-copies
+//                      (mask * w of jaxili/model.py:544, hoisted out of the step)
+//   reduce_kernel      deterministic cross-CTA sum of the per-CTA partial gradients, masked
+//                      (g_W = M * (h^T g)), plus loss and per-block squared-norm partials
+//   sqnorm_kernel      squared-norm partials of an arbitrary (e.g. all-reduced) gradient
+//   clip_adam_kernel   optax.chain(clip_by_global_norm, adam|sgd|adamw(warmup_cosine)) +
+//                      apply_gradients (jaxili/train.py:246-300, 333), refreshing the images
+#pragma once
+#include "common.cuh"
+
+namespace mafb {
+
+struct OptArgs {
+  float lr, warmup, decay_steps, init_factor, end_factor, b1, b2, eps, clip, weight_decay;
+  int kind;
+};
+
+constexpr int RED_IDX = 256;    // parameters per reduction block
+constexpr int RED_PARTS = 4;    // threads cooperating on one parameter
+
+// flat index -> (layer, linear, k, n); returns true for a bias entry
+__device__ __forceinline__ bool decode_param(const Plan& P, int idx, int& layer, int& li, int& k, int& n) {
+  layer = idx / P.ppl;
+  const int rem = idx - layer * P.ppl;
+  li = 0;
+#pragma unroll 1
+  for (int i = 0; i < P.n_lin; ++i)
+    if (rem >= P.lin[i].pw_off) li = i;
+  const LinDesc& ln = P.lin[li];
+  if (rem >= ln.pb_off) {
+    k = 0;
+    n = rem - ln.pb_off;
+    return true;
+  }
+  const int o = rem - ln.pw_off;
+  k = o / ln.N;
+  n = o - k * ln.N;
+  return false;
+}
+
+__device__ __forceinline__ void write_image(const Plan& P, float* wimg, int idx, float masked_value) {
+  int layer, li, k, n;
+  const bool is_bias = decode_param(P, idx, layer, li, k, n);
+  const LinDesc& ln = P.lin[li];
+  float* base = wimg + (size_t)layer * P.img_floats;
+  if (is_bias) {
+    base[ln.b_off + n] = masked_value;
+  } else {
+    base[ln.w_off + k * ln.NP + n] = masked_value;
+    base[P.fwd_floats + ln.wt_off + n * ln.KP + k] = masked_value;
+  }
+}
+
+__global__ void pack_kernel(const __grid_constant__ Plan P, const float* __restrict__ params,
+                            const unsigned char* __restrict__ mask, float* __restrict__ wimg) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P.P) return;
+  write_image(P, wimg, idx, mask[idx] ? params[idx] : 0.f);
+}
+
+// block: RED_IDX * RED_PARTS threads.  normpart[blockIdx] = sum of grad^2 over the block.
+__global__ void __launch_bounds__(RED_IDX * RED_PARTS)
+reduce_kernel(const float* __restrict__ partial, int G, int P, const unsigned char* __restrict__ mask,
+              float* __restrict__ grad, const float* __restrict__ partial_loss, float* __restrict__ loss,
+              float* __restrict__ normpart) {
+  __shared__ float red[RED_PARTS][RED_IDX];
+  __shared__ float wsum[RED_IDX / 32];
+  const int i = threadIdx.x % RED_IDX, p = threadIdx.x / RED_IDX;
+  const int idx = blockIdx.x * RED_IDX + i;
+  float s = 0.f;
+  if (idx < P) {
+    const float* src = partial + idx;
+#pragma unroll 4
+    for (int g = p; g < G; g += RED_PARTS) s += src[(size_t)g * P];
+  }
+  red[p][i] = s;
+  __syncthreads();
+  if (p == 0) {
+    float tot = 0.f;
+    if (idx < P) {
+      tot = ((red[0][i] + red[1][i]) + (red[2][i] + red[3][i]));
+      tot = mask[idx] ? tot : 0.f;
+      grad[idx] = tot;
+    }
+    const float sq = warp_sum(tot * tot);
+    if ((i & 31) == 0) wsum[i >> 5] = sq;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < RED_IDX / 32; ++w) t += wsum[w];
+    normpart[blockIdx.x] = t;
+  }
+  if (blockIdx.x == 0 && p == 1) {   // second part-group of block 0 reduces the loss
+    float l = 0.f;
+    for (int g = i; g < G; g += RED_IDX) l += partial_loss[g];
+    l = warp_sum(l);
+    __shared__ float lsum[RED_IDX / 32];
+    if ((i & 31) == 0) lsum[i >> 5] = l;
+    asm volatile("bar.sync 1, %0;" ::"n"(RED_IDX));
+    if (i == 0) {
+      float t = 0.f;
+      for (int w = 0; w < RED_IDX / 32; ++w) t += lsum[w];
+      loss[0] = t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RED_IDX)
+sqnorm_kernel(const float* __restrict__ grad, int P, float* __restrict__ normpart) {
+  __shared__ float wsum[RED_IDX / 32];
+  const int idx = blockIdx.x * RED_IDX + threadIdx.x;
+  const float g = idx < P ? grad[idx] : 0.f;
+  const float sq = warp_sum(g * g);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < RED_IDX / 32; ++w) t += wsum[w];
+    normpart[blockIdx.x] = t;
+  }
+}
+
+// optax.warmup_cosine_decay_schedule evaluated in FP32 at integer count t
+__device__ __forceinline__ float lr_schedule(const OptArgs& o, int t) {
+  const float tf = (float)t;
+  const float peak = o.lr, init = o.init_factor * o.lr;
+  if (tf < o.warmup) {
+    const float frac = 1.f - tf / o.warmup;
+    return (init - peak) * frac + peak;
+  }
+  const float dec = o.decay_steps - o.warmup;
+  const float tau = fminf(tf - o.warmup, dec);
+  const float cosv = 0.5f * (1.f + cosf(3.14159265358979323846f * tau / dec));
+  const float alpha = o.end_factor;
+  return peak * ((1.f - alpha) * cosv + alpha);
+}
+
+// grid: ceil(P / RED_IDX) blocks of RED_IDX threads; n_norm = number of norm partials.
+__global__ void __launch_bounds__(RED_IDX)
+clip_adam_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs O,
+                 float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ m,
+                 float* __restrict__ v, int* __restrict__ step, const float* __restrict__ normpart,
+                 int n_norm, const unsigned char* __restrict__ mask, float* __restrict__ wimg,
+                 unsigned int* __restrict__ done_counter, float* __restrict__ gnorm_out) {
+  __shared__ float wsum[RED_IDX / 32];
+  __shared__ float s_norm;
+  const int t = step[0];
+  // every block sums the norm partials in the same fixed order -> identical scale everywhere
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n_norm; i += RED_IDX) s += normpart[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < RED_IDX / 32; ++w) tot += wsum[w];
+    s_norm = sqrtf(tot);
+  }
+  __syncthreads();
+  const float gnorm = s_norm;
+  const int idx = blockIdx.x * RED_IDX + threadIdx.x;
+  if (idx < P.P) {
+    float g = grad[idx];
+    // optax.clip_by_global_norm: g if norm < max_norm else (g / norm) * max_norm
+    if (!(gnorm < O.clip)) g = (g / gnorm) * O.clip;
+    float p = params[idx];
+    const float lr_t = lr_schedule(O, t);
+    float upd;
+    if (O.kind == 1) {  // sgd (+ add_decayed_weights before it)
+      upd = g + O.weight_decay * p;
+    } else {
+      const float mm = O.b1 * m[idx] + (1.f - O.b1) * g;
+      const float vv = O.b2 * v[idx] + (1.f - O.b2) * g * g;
+      m[idx] = mm;
+      v[idx] = vv;
+      const float tn = (float)(t + 1);
+      const float mhat = mm / (1.f - powf(O.b1, tn));
+      const float vhat = vv / (1.f - powf(O.b2, tn));
+      upd = mhat / (sqrtf(vhat) + O.eps);
+      if (O.kind == 2) upd += O.weight_decay * p;  // adamw
+    }
+    p = p - lr_t * upd;
+    params[idx] = p;
+    write_image(P, wimg, idx, mask[idx] ? p : 0.f);
+  }
+  // the last block to finish bumps the optax count (all blocks have read step[0] by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(done_counter, 1u);
+    if (prev == gridDim.x - 1) {
+      step[0] = t + 1;
+      *done_counter = 0u;
+      if (gnorm_out) gnorm_out[0] = gnorm;
+    }
+  }
+}
+
+// FP32 FFMA throughput probe with the operand pattern of the register-tiled GEMM inner loops:
+// acc[j][i] = fma(a[i], w[j], acc[j][i]) on 16 independent accumulators, all-register operands.
+__global__ void ffma_peak_kernel(float* out, int iters, float seed) {
+  float a[4], w[4], acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a[i] = seed * (float)(threadIdx.x + i + 1);
+    w[i] = seed * (float)(threadIdx.x * 3 + i + 1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j][i] = (float)(i + j);
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(a[i], w[j], acc[j][i]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += acc[j][i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace mafb

@@ -1,0 +1,197 @@
+"""MafEngine: thin host wrapper around one native ``mafb200_handle``.
+
+Device memory, streams and (elsewhere) ``torch.distributed`` are torch's; every FLOP
+of the hot path runs in the hand-written sm_100a kernels behind the C ABI.  All
+tensors are FP32, contiguous, on the engine's CUDA device; calls enqueue on torch's
+current stream and do not synchronise.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .masks import maf_degrees
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class MafEngine:
+    """One ConditionalMAF (+ standardisation constants) bound to one GPU."""
+
+    def __init__(self, n_in, n_cond, n_layers, layers, activation="relu", use_reverse=True,
+                 seed=42, shift=None, scale=None, mean=None, std=None, device=None):
+        if activation not in _lib.ACTIVATIONS:
+            raise ValueError(
+                f"activation {activation!r} is not supported by the fused kernels; "
+                f"choose one of {sorted(_lib.ACTIVATIONS)}")
+        if not (1 <= len(layers) <= _lib.MAX_HIDDEN):
+            raise ValueError("layers must have between 1 and 5 entries")
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.MafB200Error("no CUDA device: jaxili_b200 has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device) \
+            if not isinstance(device, torch.device) else device
+        self.n_in, self.n_cond, self.n_layers = int(n_in), int(n_cond), int(n_layers)
+        self.layers = [int(h) for h in layers]
+        self.activation, self.use_reverse, self.seed = activation, bool(use_reverse), seed
+        self.degrees = maf_degrees(self.n_in, self.layers, self.n_layers, seed)
+        desc = _lib.MafDesc()
+        desc.n_in, desc.n_cond, desc.n_layers = self.n_in, self.n_cond, self.n_layers
+        desc.n_hidden = len(self.layers)
+        for i, h in enumerate(self.layers):
+            desc.hidden[i] = h
+        desc.activation = _lib.ACTIVATIONS[activation]
+        desc.use_reverse = int(self.use_reverse)
+        self._std = [_f32(shift), _f32(scale), _f32(mean), _f32(std)]
+        handle = C.c_void_p()
+        _lib.check(self.lib.mafb200_create(
+            C.byref(desc), self.degrees.ctypes.data_as(C.c_void_p),
+            *[_np_ptr(a) for a in self._std], self.device.index, C.byref(handle)))
+        self._h = handle
+        self.n_params = int(self.lib.mafb200_param_count(self._h))
+        self.dims = [self.n_in + self.n_cond, *self.layers, 2 * self.n_in]
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self.lib.mafb200_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _chk(self, t, name, cols=None):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise TypeError(f"{name} must be a contiguous float32 CUDA tensor")
+        if t.device != self.device:
+            raise ValueError(f"{name} is on {t.device}, engine is on {self.device}")
+        if t.data_ptr() % 16:
+            raise ValueError(f"{name} must be 16-byte aligned")
+        if cols is not None and (t.dim() != 2 or t.shape[1] != cols):
+            raise ValueError(f"{name} must have shape (rows, {cols}), got {tuple(t.shape)}")
+        return C.c_void_p(t.data_ptr())
+
+    def set_standardization(self, shift=None, scale=None, mean=None, std=None):
+        self._std = [_f32(shift), _f32(scale), _f32(mean), _f32(std)]
+        _lib.check(self.lib.mafb200_set_standardization(self._h, *[_np_ptr(a) for a in self._std]))
+
+    def mask(self):
+        """0/1 uint8 vector in flat parameter order (biases 1)."""
+        m = np.empty(self.n_params, dtype=np.uint8)
+        _lib.check(self.lib.mafb200_get_mask(self._h, m.ctypes.data_as(C.c_void_p)))
+        return m
+
+    def query(self):
+        v = [C.c_int32() for _ in range(4)]
+        _lib.check(self.lib.mafb200_query(self._h, *[C.byref(a) for a in v]))
+        return dict(smem_bytes=v[0].value, tile_rows=v[1].value, max_ctas=v[2].value, stash_all=v[3].value)
+
+    # ------------------------------------------------------------------ hot path
+    def pack(self, params):
+        _lib.check(self.lib.mafb200_pack(self._h, self._chk(params, "params"), self._stream()))
+
+    def log_prob(self, params, x, y, out=None, packed_current=False):
+        px = self._chk(x, "x", self.n_in)
+        py = self._chk(y, "y", self.n_cond) if self.n_cond else None
+        B = x.shape[0]
+        if self.n_cond and y.shape[0] != B:
+            raise ValueError("x and y must have the same number of rows")
+        if out is None:
+            out = torch.empty(B, dtype=torch.float32, device=self.device)
+        if B:
+            _lib.check(self.lib.mafb200_log_prob(
+                self._h, self._chk(params, "params"), px, py, B, self._chk(out, "out"),
+                _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
+        return out
+
+    def loss_grad(self, params, x, y, out_loss, out_grad, batch_rows=None, inv_global_b=None,
+                  batch_index=None, n_batches=1, packed_current=False):
+        """out_loss[0], out_grad <- NLL and its gradient over rows [0, batch_rows) of x/y (or the
+        device-selected batch ``batch_index[0] % n_batches``)."""
+        px = self._chk(x, "x", self.n_in)
+        py = self._chk(y, "y", self.n_cond) if self.n_cond else None
+        B = x.shape[0] if batch_rows is None else int(batch_rows)
+        if batch_index is not None:
+            if x.shape[0] < B * n_batches:
+                raise ValueError("x holds fewer than n_batches * batch_rows rows")
+            bi = C.c_void_p(batch_index.data_ptr())
+        else:
+            bi = None
+        inv = 1.0 / B if inv_global_b is None else float(inv_global_b)
+        _lib.check(self.lib.mafb200_loss_grad(
+            self._h, self._chk(params, "params"), px, py, B, inv, bi, int(n_batches),
+            self._chk(out_loss, "out_loss"), self._chk(out_grad, "out_grad"),
+            _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
+
+    @staticmethod
+    def make_opt_desc(lr=1e-3, warmup=0.0, decay_steps=1e9, clip=5.0, b1=0.9, b2=0.999, eps=1e-8,
+                      weight_decay=0.0, kind="adam", init_factor=0.01, end_factor=0.01):
+        o = _lib.MafOptDesc()
+        o.lr, o.warmup, o.decay_steps = lr, warmup, decay_steps
+        o.init_factor, o.end_factor = init_factor, end_factor
+        o.b1, o.b2, o.eps, o.clip, o.weight_decay = b1, b2, eps, clip, weight_decay
+        o.kind = {"adam": 0, "sgd": 1, "adamw": 2}[kind]
+        return o
+
+    def clip_adam(self, params, grad, m, v, step, opt, norm_current=False):
+        """In-place optax-chain update; ``step`` is an int32 CUDA tensor (the optax count)."""
+        if step.dtype != torch.int32 or not step.is_cuda:
+            raise TypeError("step must be an int32 CUDA tensor")
+        _lib.check(self.lib.mafb200_clip_adam(
+            self._h, self._chk(params, "params"), self._chk(grad, "grad"),
+            self._chk(m, "m") if m is not None else None, self._chk(v, "v") if v is not None else None,
+            C.c_void_p(step.data_ptr()), C.byref(opt), _lib.NORM_CURRENT if norm_current else 0,
+            self._stream()))
+
+    def sample_from_noise(self, params, u, y_obs, rows_per_obs=None, out=None, packed_current=False):
+        pu = self._chk(u, "u", self.n_in)
+        N = u.shape[0]
+        y_obs = y_obs.reshape(-1, self.n_cond) if self.n_cond else y_obs
+        n_obs = y_obs.shape[0] if self.n_cond else 1
+        if rows_per_obs is None:
+            rows_per_obs = max(1, -(-N // n_obs))
+        if out is None:
+            out = torch.empty_like(u)
+        if N:
+            _lib.check(self.lib.mafb200_sample_from_noise(
+                self._h, self._chk(params, "params"), pu,
+                self._chk(y_obs, "y_obs") if self.n_cond else None, n_obs, int(rows_per_obs), N,
+                self._chk(out, "out"), _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
+        return out
+
+    def sample_philox(self, params, N, y_obs, seed=0, row_offset=0, rows_per_obs=None, out=None,
+                      packed_current=False):
+        y_obs = y_obs.reshape(-1, self.n_cond) if self.n_cond else y_obs
+        n_obs = y_obs.shape[0] if self.n_cond else 1
+        if rows_per_obs is None:
+            rows_per_obs = max(1, -(-N // n_obs))
+        if out is None:
+            out = torch.empty((N, self.n_in), dtype=torch.float32, device=self.device)
+        if N:
+            _lib.check(self.lib.mafb200_sample_philox(
+                self._h, self._chk(params, "params"), int(seed) & (2**64 - 1), int(row_offset),
+                self._chk(y_obs, "y_obs") if self.n_cond else None, n_obs, int(rows_per_obs), int(N),
+                self._chk(out, "out"), _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
+        return out
+
+
+def ffma_peak_tflops(device=0, iters=4096):
+    """Measured FP32 FFMA throughput of the GPU (register-tiled GEMM operand pattern)."""
+    lib = _lib.load()
+    out = C.c_float()
+    _lib.check(lib.mafb200_ffma_peak(int(device), int(iters), C.byref(out)))
+    return float(out.value)
