@@ -15,6 +15,8 @@
  *                                jaxili/train.py:330-332, jaxili/loss.py:35-83
  *   mafb200_clip_adam         <- state.apply_gradients(grads) with the optax chain built in
  *                                jaxili/train.py:246-300 (clip_by_global_norm -> adam(warmup_cosine))
+ *   mafb200_forward           <- ConditionalMAF.__call__ (u, log_det)  jaxili/model.py:848-874
+ *   mafb200_inverse           <- ConditionalMAF.backward (x, log_det)  jaxili/model.py:876-901
  *   mafb200_sample_from_noise <- model.apply(..., method="sample") with the base noise given
  *   mafb200_sample_philox        jaxili/model.py:1116-1126 -> 923-947 -> 876-901 -> 745-773
  *                                (caller: jaxili/posterior/direct_posterior.py:70-72)
@@ -111,6 +113,10 @@ int mafb200_destroy(mafb200_handle h);
 int mafb200_set_standardization(mafb200_handle h, const float* shift, const float* scale,
                                 const float* mean, const float* std);
 
+/* debug: phase-boundary clock stamps of CTA 0 of the flow kernel go to this device buffer of
+   1001 int64 ((id, clock) pairs, count at [1000]); NULL switches tracing off (default). */
+int mafb200_debug_trace(mafb200_handle h, long long* trace_dev);
+
 int64_t mafb200_param_count(mafb200_handle h);
 /* writes the 0/1 mask in flat parameter order (biases 1) to a host buffer of param_count bytes */
 int mafb200_get_mask(mafb200_handle h, uint8_t* mask_host);
@@ -124,6 +130,13 @@ int mafb200_pack(mafb200_handle h, const float* params, void* stream);
 /* out_logp[b] = log p(x_b | y_b), b < B.  x: B x n_in, y: B x n_cond. */
 int mafb200_log_prob(mafb200_handle h, const float* params, const float* x, const float* y,
                      int64_t B, float* out_logp, int32_t flags, void* stream);
+
+/* ConditionalMAF.__call__ (jaxili/model.py:848-874): any of out_logp [B], out_u [B x n_in]
+   (base-space point after the last flip) and out_logdet [B] (summed MAF log|det J|, without
+   the standardisation constant) may be NULL. */
+int mafb200_forward(mafb200_handle h, const float* params, const float* x, const float* y,
+                    int64_t B, float* out_logp, float* out_u, float* out_logdet,
+                    int32_t flags, void* stream);
 
 /* out_loss[0] = -inv_global_B * sum_b log p(x_b|y_b); out_grad = d out_loss / d params
    (P floats, masked entries exactly 0).  If batch_index != NULL the batch is rows
@@ -145,6 +158,10 @@ int mafb200_clip_adam(mafb200_handle h, float* params, const float* grad, float*
 int mafb200_sample_from_noise(mafb200_handle h, const float* params, const float* u,
                               const float* y_obs, int64_t n_obs, int64_t rows_per_obs,
                               int64_t N, float* out, int32_t flags, void* stream);
+/* ConditionalMAF.backward (jaxili/model.py:876-901): per-row conditioning y [N x n_cond];
+   out_x [N x n_in], out_logdet [N] = sum over layers of sum_d min(-logp_d/2, 10) (nullable). */
+int mafb200_inverse(mafb200_handle h, const float* params, const float* u, const float* y,
+                    int64_t N, float* out_x, float* out_logdet, int32_t flags, void* stream);
 /* same with u ~ N(0,I) drawn in-kernel: Philox4x32-10, subsequence = row_offset + r */
 int mafb200_sample_philox(mafb200_handle h, const float* params, uint64_t seed,
                           uint64_t row_offset, const float* y_obs, int64_t n_obs,

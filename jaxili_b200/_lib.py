@@ -49,12 +49,17 @@ SYMBOLS = {
                                  C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "mafb200_destroy": (C.c_int, [C.c_void_p]),
     "mafb200_set_standardization": (C.c_int, [C.c_void_p] * 5),
+    "mafb200_debug_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mafb200_param_count": (C.c_int64, [C.c_void_p]),
     "mafb200_get_mask": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mafb200_query": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int32)] * 4),
     "mafb200_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mafb200_log_prob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p, C.c_int32, C.c_void_p]),
+    "mafb200_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mafb200_inverse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mafb200_loss_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_float, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                     C.c_int32, C.c_void_p]),

@@ -129,79 +129,143 @@ __device__ __forceinline__ void act_eval(int act, float a, float& h, float& d) {
 
 // out[c][r] = sum_q in[q][r] * m[q][c]   for r in r0..r0+TM-1, c in c0..c0+TN-1
 // in: [Q][RP] feature-major, m: [Q][CP] row-major.  Per q: one TM-wide and one TN-wide vector
-// load feed TM*TN FFMAs.  Used for the forward linears (m = masked W) and for the
-// input-gradient products (in = G, m = masked W^T).
-template <int TM, int TN, class Epi>
-__device__ __forceinline__ void mm_outer(const float* __restrict__ in, int Q, int RP,
-                                         const float* __restrict__ m, int CP, int r0, int c0,
-                                         Epi&& epi) {
-  float acc[TN][TM];
+// load feed TM*TN FFMAs.  Only q = q0, q0+qs, q0+2qs, ... are visited (lane-group split of the
+// reduction; qs = 1 for the whole sum).
+template <int TM, int TN>
+__device__ __forceinline__ void mm_outer_acc(float (&acc)[TN][TM], const float* __restrict__ in, int Q,
+                                             int RP, const float* __restrict__ m, int CP, int r0, int c0,
+                                             int q0, int qs) {
 #pragma unroll
   for (int j = 0; j < TN; ++j)
 #pragma unroll
     for (int i = 0; i < TM; ++i) acc[j][i] = 0.f;
-  const float* a = in + r0;
-  const float* w = m + c0;
+  const float* a = in + r0 + q0 * RP;
+  const float* w = m + c0 + q0 * CP;
+  const int da = qs * RP, dw = qs * CP;
 #pragma unroll 4
-  for (int q = 0; q < Q; ++q) {
+  for (int q = q0; q < Q; q += qs) {
     float av[TM], wv[TN];
     ldv(av, a);
     ldv(wv, w);
-    a += RP;
-    w += CP;
+    a += da;
+    w += dw;
 #pragma unroll
     for (int j = 0; j < TN; ++j)
 #pragma unroll
       for (int i = 0; i < TM; ++i) acc[j][i] = fmaf(av[i], wv[j], acc[j][i]);
   }
+}
+
+template <int TM, int TN, class Epi>
+__device__ __forceinline__ void mm_outer(const float* __restrict__ in, int Q, int RP,
+                                         const float* __restrict__ m, int CP, int r0, int c0,
+                                         Epi&& epi) {
+  float acc[TN][TM];
+  mm_outer_acc<TM, TN>(acc, in, Q, RP, m, CP, r0, c0, 0, 1);
   epi(acc);
 }
 
-// dW[k][n] = sum_r A[k][r] * G[n][r]  for the TK x TN strided tile k = kb + i*nKB, n = nb + j*nNB.
-// The strided assignment makes the TK (TN) row loads of one warp instruction hit consecutive
-// feature rows, which the RP pitch maps to distinct banks.
-template <int TK, int TN>
-__device__ __forceinline__ void mm_inner(const float* __restrict__ A, int K, const float* __restrict__ G,
-                                         int N, int Rt, int RP, int kb, int nKB, int nb, int nNB,
-                                         float* __restrict__ out, bool accumulate) {
-  float acc[TK][TN];
-  const float* ap[TK];
-  const float* gp[TN];
+// 4-way lane-group split of the reduction for a 4x4 tile.  The four lanes {l, l^8, l^16, l^24}
+// hold partial sums of the same tile (kq = (lane>>3)&3 selects q = kq, kq+4, ...).  A warp-shuffle
+// reduce-scatter leaves lane kq with the complete sums of tile column kq (4 rows) in res[].
+__device__ __forceinline__ void reduce_scatter4(const float (&acc)[4][4], int kq, float (&res)[4]) {
+  const bool b1 = (kq & 2) != 0, b0 = (kq & 1) != 0;
+  float t[2][4];
 #pragma unroll
-  for (int i = 0; i < TK; ++i) {
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = b1 ? acc[c][i] : acc[2 + c][i];
+      const float mine = b1 ? acc[2 + c][i] : acc[c][i];
+      t[c][i] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b0 ? t[0][i] : t[1][i];
+    const float mine = b0 ? t[1][i] : t[0][i];
+    res[i] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+}
+
+// 2-way variant: lanes {l, l^16} hold partial sums of the same 4x4 tile (kq = lane>>4 takes
+// q = kq, kq+2, ...); lane kq ends with complete sums of tile columns 2kq, 2kq+1 in res[2][4].
+__device__ __forceinline__ void reduce_scatter2(const float (&acc)[4][4], int kq, float (&res)[2][4]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = kq ? acc[c][i] : acc[2 + c][i];
+      const float mine = kq ? acc[2 + c][i] : acc[c][i];
+      res[c][i] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+}
+
+// dW[k][n] = sum_r A[row(k)][r] * G[n][r] for the 4x4 strided tile k = kb + i*nKB, n = nb + j*nNB,
+// k in [0, K]: row(k) = k for k < K and ones_row for k == K (a feature row of ones, which makes
+// dW[K][n] the bias gradient; the flat layout stores the bias right behind the kernel).
+// The row dimension is split over the two half-warps (rh = lane>>4 takes r = 4rh, 4rh+8, ...) and
+// combined with a warp-shuffle reduce-scatter: half rh ends up owning tile rows i = 2rh, 2rh+1.
+// The strided k/n assignment makes the row loads of one warp instruction hit consecutive feature
+// rows, which the RP pitch maps to distinct banks.
+__device__ __forceinline__ void mm_inner_rs2(const float* __restrict__ A, int K, int ones_row,
+                                             const float* __restrict__ G, int N, int Rt, int RP, int kb,
+                                             int nKB, int nb, int nNB, int rh, bool store,
+                                             float* __restrict__ out, bool accumulate) {
+  float acc[4][4];
+  const float* ap[4];
+  const float* gp[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
     const int k = kb + i * nKB;
-    ap[i] = A + (k < K ? k : K - 1) * RP;
+    ap[i] = A + (k < K ? k : ones_row) * RP + 4 * rh;
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   }
 #pragma unroll
-  for (int j = 0; j < TN; ++j) {
+  for (int j = 0; j < 4; ++j) {
     const int n = nb + j * nNB;
-    gp[j] = G + (n < N ? n : N - 1) * RP;
+    gp[j] = G + (n < N ? n : N - 1) * RP + 4 * rh;
   }
 #pragma unroll 2
-  for (int r = 0; r < Rt; r += 4) {
-    float av[TK][4], gv[TN][4];
+  for (int r = 4 * rh; r < Rt; r += 8) {
+    float av[4][4], gv[4][4];
 #pragma unroll
-    for (int i = 0; i < TK; ++i) ldv(av[i], ap[i] + r);
+    for (int i = 0; i < 4; ++i) { ldv(av[i], ap[i]); ap[i] += 8; }
 #pragma unroll
-    for (int j = 0; j < TN; ++j) ldv(gv[j], gp[j] + r);
+    for (int j = 0; j < 4; ++j) { ldv(gv[j], gp[j]); gp[j] += 8; }
 #pragma unroll
-    for (int i = 0; i < TK; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < TN; ++j)
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int t = 0; t < 4; ++t) acc[i][j] = fmaf(av[i][t], gv[j][t], acc[i][j]);
   }
+  // reduce-scatter across the half-warps: keep tile rows 2rh, 2rh+1
+  float res[2][4];
 #pragma unroll
-  for (int i = 0; i < TK; ++i) {
-    const int k = kb + i * nKB;
+  for (int c = 0; c < 2; ++c)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const int n = nb + j * nNB;
-      if (k < K && n < N) {
-        float* p = out + k * N + n;
-        *p = accumulate ? *p + acc[i][j] : acc[i][j];
+    for (int j = 0; j < 4; ++j) {
+      const float send = rh ? acc[c][j] : acc[2 + c][j];
+      const float mine = rh ? acc[2 + c][j] : acc[c][j];
+      res[c][j] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  if (store) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int k = kb + (2 * rh + c) * nKB;
+      if (k <= K) {
+        float* prow = out + k * N;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = nb + j * nNB;
+          if (n < N) {
+            // this thread is the only writer of its entries of the CTA's partial-gradient slice;
+            // later tiles add with a fire-and-forget reduction (no load latency, same order each run)
+            if (accumulate) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(prow + n), "f"(res[c][j]) : "memory");
+            else prow[n] = res[c][j];
+          }
+        }
       }
     }
   }

@@ -25,20 +25,28 @@ struct FlowArgs {
   const float* stdc;          // [shift D][inv_scale D][mean C][std C]
   float logdet_const;         // sum_i -log|scale_i|
   float inv_b;                // 1 / global batch size
-  float* out_logp;            // forward-only: [B]
+  float* out_logp;            // forward-only: [B] (nullable)
+  float* out_u;               // forward-only: [B][D] base-space point u (nullable)
+  float* out_logdet;          // forward-only: [B] summed log|det J| of the MAF (nullable)
   float* partial_grad;        // training: [grid][P]
   float* partial_loss;        // training: [grid]
   int Rt;                     // rows per tile in this launch (multiple of 4, <= Plan::R)
+  int rb_shift;               // log2 of the power of two >= Rt/4 (row blocks per warp slot group)
   int n_tiles;
+  long long* trace;           // debug: clock64 stamps of CTA 0 at phase boundaries (nullable)
 };
 
-constexpr int FM = 4, FN = 2;   // forward tile: rows x cols per thread
-constexpr int XM = 4, XN = 4;   // input-gradient tile
-constexpr int BK = 4, BN = 4;   // weight-gradient tile
+// Every micro-GEMM uses 4x4 register tiles.  The reduction dimension is split over lane groups
+// of a warp (4 ways for the forward / input-gradient products, 2 ways for the weight-gradient
+// products) and recombined with warp-shuffle reduce-scatters: more parallel work units and
+// shorter dependent chains than one tile per thread, which is what the small per-SM row count
+// (28 rows at B=4096) needs.  Work units are mapped to (warp, lane) with shifts and masks only.
+constexpr int TS = 4;           // tile side
+constexpr int KS = 4;           // lane groups splitting the reduction of outer-form products
 constexpr float kHalfLog2Pi = 0.9189385332046727f;
 
 template <bool BWD, bool RELU, int NT>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1)
 maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* wbar = reinterpret_cast<uint64_t*>(smem_raw);   // [2] weight images
@@ -50,7 +58,15 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
   constexpr int NW = NT / 32;
   const int D = P.D, C = P.C, L = P.L, RP = P.RP, n_lin = P.n_lin;
   const int Rt = A.Rt;
-  const int nRB = Rt / FM;
+  const int nRB = Rt / TS;
+  // outer-form products: a warp holds 8 tile slots x 4 reduction lanes; slot -> (row block, col block)
+  const int kq = lane >> 3;
+  const int slot8 = lane & 7;
+  const int o_rb = slot8 & ((1 << A.rb_shift) - 1);
+  const int o_cbl = slot8 >> A.rb_shift;          // column block within the warp's group
+  const int o_cpw = 8 >> A.rb_shift;              // column blocks per warp
+  const bool o_rok = o_rb < nRB;
+  const int o_r0 = (o_rok ? o_rb : 0) * TS;
   const long long row_base =
       A.batch_index ? (long long)(A.batch_index[0] % A.n_batches) * A.B : 0;
   const int grid = gridDim.x;
@@ -66,11 +82,26 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
   }
   __syncthreads();
 
+#ifdef MAFB_TRACE
+  int n_trace = 0;
+  auto stamp = [&](int id) {
+    if (A.trace && blockIdx.x == 0 && tid == 0 && n_trace < 500) {
+      A.trace[2 * n_trace] = id;
+      A.trace[2 * n_trace + 1] = clock64();
+      ++n_trace;
+    }
+  };
+#else
+  auto stamp = [](int) {};
+#endif
+  stamp(0);
+
   const bool recompute = BWD && !P.stash_all;
   const int per_tile = BWD ? 2 * L : L;
   const int total_req = my_n * per_tile;
 
-  // ---- weight image requests: s-th request of this CTA (thread 0 only)
+  // ---- weight image requests: s-th request of this CTA.  Issued by the last warp's lane 0 (that
+  //      warp is the least loaded in every phase) so the issue latency stays off the critical path.
   auto w_issue = [&](int s) {
     const int j = s % per_tile;
     int layer, part;
@@ -81,14 +112,15 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
     else if (recompute) bytes = P.img_floats * 4u;
     else { src += P.fwd_floats; bytes = P.bwd_floats * 4u; }
     const int buf = s % P.n_wbuf;
-    fence_proxy_async();
     mbar_expect_tx(&wbar[buf], bytes);
     bulk_g2s(sm + P.o_wbuf + buf * P.wbuf_stride, src, bytes, &wbar[buf]);
   };
-  // every thread: make request s resident, prefetch s+1; returns the buffer
+  const bool issuer = tid == NT - 32;
+  // every thread: make request s resident, prefetch s+1; returns the buffer.  The buffer being
+  // refilled was last read before the __syncthreads that precedes this call.
   auto w_acquire = [&](int s) -> const float* {
     const int buf = s % P.n_wbuf;
-    if (tid == 0) {
+    if (issuer) {
       if (P.n_wbuf == 1) w_issue(s);
       else if (s + 1 < total_req) w_issue(s + 1);
     }
@@ -107,8 +139,7 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
     const bool fast = (valid % 4 == 0) && ((reinterpret_cast<uintptr_t>(xs) & 15) == 0) &&
                       (C == 0 || (reinterpret_cast<uintptr_t>(ys) & 15) == 0);
     if (fast) {
-      if (tid == 0) {
-        fence_proxy_async();
+      if (issuer) {
         mbar_expect_tx(&sbar[i & 1], (uint32_t)(valid * (D + C) * 4));
         bulk_g2s(dst, xs, (uint32_t)(valid * D * 4), &sbar[i & 1]);
         if (C) bulk_g2s(dst + P.R * D, ys, (uint32_t)(valid * C * 4), &sbar[i & 1]);
@@ -116,21 +147,31 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
     } else {
       for (int idx = tid; idx < valid * D; idx += NT) dst[idx] = xs[idx];
       for (int idx = tid; idx < valid * C; idx += NT) dst[P.R * D + idx] = ys[idx];
-      if (tid == 0) mbar_arrive(&sbar[i & 1]);
+      if (issuer) mbar_arrive(&sbar[i & 1]);
     }
   };
 
-  if (tid == 0 && P.n_wbuf == 2 && total_req > 0) w_issue(0);
+  if (issuer && P.n_wbuf == 2 && total_req > 0) w_issue(0);
   if (my_n > 0) stage_issue(0);
 
   float* const obuf = sm + P.o_obuf;
   float* const gu = sm + P.o_gu;
   float* const gx = sm + P.o_gx;
   float* const ld = sm + P.o_ld;
-  const float* const c_shift = A.stdc;
-  const float* const c_iscale = A.stdc + D;
-  const float* const c_mean = A.stdc + 2 * D;
-  const float* const c_std = A.stdc + 2 * D + C;
+  float* const cst = sm + P.o_cst;   // [shift D][inv_scale D][mean C][std C]
+  for (int idx = tid; idx < 2 * D + 2 * C; idx += NT) cst[idx] = A.stdc[idx];
+
+  if (BWD) {
+    // a feature row of ones behind every weight-gradient A operand: [A;1]^T G yields the bias
+    // gradient as one more row of the weight-gradient product.  Written once, never overwritten.
+    const int n_slots = P.stash_all ? L : 1;
+    for (int idx = tid; idx < RP; idx += NT) {
+      for (int l = 0; l < L; ++l) sm[P.o_xin + l * P.xin_stride + P.lin[0].KP * RP + idx] = 1.f;
+      for (int sl = 0; sl < n_slots; ++sl)
+        for (int i = 1; i < n_lin; ++i)
+          sm[P.o_slot + sl * P.slot_stride + P.h_off[i] + P.lin[i].KP * RP + idx] = 1.f;
+    }
+  }
 
   // ---- one MADE + affine transform.  replay: recomputation inside the reverse pass
   //      (no log-det accumulation, no hand-off of v to the next layer).
@@ -140,60 +181,62 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
       const LinDesc& ln = P.lin[i];
       const float* W = wf + ln.w_off;
       const float* bias = wf + ln.b_off;
-      const int items = nRB * (ln.NP / FN);
-      if (i < n_lin - 1) {
-        float* hout = slot + P.h_off[i + 1];
-        float* dout = slot + P.d_off[i + 1];
-        for (int it = tid; it < items; it += NT) {
-          const int r0 = (it % nRB) * FM, c0 = (it / nRB) * FN;
-          mm_outer<FM, FN>(in, ln.K, RP, W, ln.NP, r0, c0, [&](float (&acc)[FN][FM]) {
+      const int nCB = ln.NP / TS;
+      const int Q = ln.K, CP = ln.NP;
+      const bool last = i == n_lin - 1;
+      float* hout = last ? obuf : slot + P.h_off[i + 1];
+      float* dout = slot + P.d_off[last ? 1 : i + 1];
+      for (int cb0 = warp * o_cpw; cb0 < nCB; cb0 += NW * o_cpw) {
+        const int cb = cb0 + o_cbl;
+        const bool ok = o_rok && cb < nCB;
+        const int c0 = (cb < nCB ? cb : nCB - 1) * TS;
+        float acc[TS][TS], res[TS];
+        stamp(30);
+        mm_outer_acc<TS, TS>(acc, in, Q, RP, W, CP, o_r0, c0, kq, KS);
+        stamp(31);
+        reduce_scatter4(acc, kq, res);
+        stamp(32);
+        if (ok) {   // lane kq finishes tile column kq
+          const int c = c0 + kq;
+          const float bj = bias[c];
+          if (!last) {
+            float hv[TS], dv[TS];
 #pragma unroll
-            for (int j = 0; j < FN; ++j) {
-              const float bj = bias[c0 + j];
-              float hv[FM], dv[FM];
+            for (int q = 0; q < TS; ++q) act_eval<RELU>(P.act, res[q] + bj, hv[q], dv[q]);
+            stv(hout + c * RP + o_r0, hv);
+            if (!RELU && BWD) stv(dout + c * RP + o_r0, dv);
+          } else {
+            float ov[TS];
 #pragma unroll
-              for (int q = 0; q < FM; ++q) act_eval<RELU>(P.act, acc[j][q] + bj, hv[q], dv[q]);
-              stv(hout + (c0 + j) * RP + r0, hv);
-              if (!RELU && BWD) stv(dout + (c0 + j) * RP + r0, dv);
-            }
-          });
-        }
-        in = hout;
-      } else {
-        for (int it = tid; it < items; it += NT) {
-          const int r0 = (it % nRB) * FM, c0 = (it / nRB) * FN;
-          mm_outer<FM, FN>(in, ln.K, RP, W, ln.NP, r0, c0, [&](float (&acc)[FN][FM]) {
-#pragma unroll
-            for (int j = 0; j < FN; ++j) {
-              const float bj = bias[c0 + j];
-              float ov[FM];
-#pragma unroll
-              for (int q = 0; q < FM; ++q) ov[q] = acc[j][q] + bj;
-              stv(obuf + (c0 + j) * RP + r0, ov);
-            }
-          });
+            for (int q = 0; q < TS; ++q) ov[q] = res[q] + bj;
+            stv(hout + c * RP + o_r0, ov);
+          }
         }
       }
+      in = hout;
+      stamp(33);
       __syncthreads();
+      stamp(10 + i);
     }
-    // affine autoregressive transform (jaxili/model.py:739-742)
+    // affine autoregressive transform (jaxili/model.py:739-742): lane = row, warp strides features
     const float* xin = sm + P.o_xin + k * P.xin_stride;
     float* xnext = (k + 1 < L) ? sm + P.o_xin + (k + 1) * P.xin_stride : gu;
     float* sbuf = slot + P.s_off;
     float* vbuf = slot + P.v_off;
-    for (int idx = tid; idx < D * Rt; idx += NT) {
-      const int j = idx / Rt, r = idx - j * Rt;
-      const float mu = obuf[j * RP + r], lp = obuf[(D + j) * RP + r];
-      const float s = expf(0.5f * lp);
-      const float v = (xin[j * RP + r] - mu) * s;
-      if (BWD) { sbuf[j * RP + r] = s; vbuf[j * RP + r] = v; }
-      if (!replay) {
-        ld[j * RP + r] += 0.5f * lp;
-        const int jj = P.reverse ? D - 1 - j : j;
-        xnext[jj * RP + r] = v;
+    for (int r = lane; r < Rt; r += 32)
+      for (int j = warp; j < D; j += NW) {
+        const float mu = obuf[j * RP + r], lp = obuf[(D + j) * RP + r];
+        const float s = expf(0.5f * lp);
+        const float v = (xin[j * RP + r] - mu) * s;
+        if (BWD) { sbuf[j * RP + r] = s; vbuf[j * RP + r] = v; }
+        if (!replay) {
+          ld[j * RP + r] += 0.5f * lp;
+          const int jj = P.reverse ? D - 1 - j : j;
+          xnext[jj * RP + r] = v;
+        }
       }
-    }
     __syncthreads();
+    stamp(19);
   };
 
   for (int ti = 0; ti < my_n; ++ti) {
@@ -205,54 +248,74 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
     // ---- stage in: wait for the bulk copy, transpose to feature-major, standardise
     mbar_wait(&sbar[ti & 1], (uint32_t)((ti >> 1) & 1));
     __syncthreads();
+    stamp(1);
     {
       const float* st = sm + P.o_stage + (ti & 1) * P.stage_stride;
       float* xin0 = sm + P.o_xin;
-      for (int idx = tid; idx < D * Rt; idx += NT) {
-        const int j = idx / Rt, r = idx - j * Rt;
-        // distrax.ScalarAffine.inverse: (x - shift) * (1/scale)
-        xin0[j * RP + r] = r < valid ? (st[r * D + j] - c_shift[j]) * c_iscale[j] : 0.f;
+      for (int r = lane; r < Rt; r += 32) {
+        const bool ok = r < valid;
+        for (int j = warp; j < D + C; j += NW) {
+          if (j < D) {
+            // distrax.ScalarAffine.inverse: (x - shift) * (1/scale)
+            xin0[j * RP + r] = ok ? (st[r * D + j] - cst[j]) * cst[D + j] : 0.f;
+            ld[j * RP + r] = 0.f;
+          } else {
+            // Standardizer: (y - mean) / std
+            const int c = j - D;
+            const float v = ok ? __fdiv_rn(st[P.R * D + r * C + c] - cst[2 * D + c], cst[2 * D + C + c]) : 0.f;
+            for (int l = 0; l < L; ++l) sm[P.o_xin + l * P.xin_stride + j * RP + r] = v;
+          }
+        }
       }
-      for (int idx = tid; idx < C * Rt; idx += NT) {
-        const int c = idx / Rt, r = idx - c * Rt;
-        // Standardizer: (y - mean) / std
-        const float v = r < valid ? __fdiv_rn(st[P.R * D + r * C + c] - c_mean[c], c_std[c]) : 0.f;
-        for (int l = 0; l < L; ++l) sm[P.o_xin + l * P.xin_stride + (D + c) * RP + r] = v;
-      }
-      for (int idx = tid; idx < P.DP * RP; idx += NT) ld[idx] = 0.f;
     }
     __syncthreads();
+    stamp(2);
     if (ti + 1 < my_n) stage_issue(ti + 1);
 
     // ---- forward through the L MAF layers
     for (int k = 0; k < L; ++k) {
       const float* wf = w_acquire(req++);
+      stamp(3);
       float* slot = sm + P.o_slot + ((BWD && P.stash_all) ? k : 0) * P.slot_stride;
       layer_forward(k, wf, slot, false);
     }
 
     // ---- log-probability per row (jaxili/model.py:919-921 + 1094-1098); seed of the reverse pass
-    for (int r = tid; r < Rt; r += NT) {
-      float acc = 0.f;
-      for (int j = 0; j < D; ++j) {
-        const float u = gu[j * RP + r];
-        acc += ld[j * RP + r] - 0.5f * u * u;
-        if (BWD) gu[j * RP + r] = r < valid ? u * A.inv_b : 0.f;
-      }
+    for (int r = tid; r < ((Rt + 31) & ~31); r += NT) {   // whole warps: lane = row
+      float acc = 0.f, ldsum = 0.f;
+      if (r < Rt)
+        for (int j = 0; j < D; ++j) {
+          const float u = gu[j * RP + r];
+          const float l = ld[j * RP + r];
+          ldsum += l;
+          acc += l - 0.5f * u * u;
+          if (BWD) gu[j * RP + r] = r < valid ? u * A.inv_b : 0.f;
+        }
       const float lp = acc - (float)D * kHalfLog2Pi + A.logdet_const;
       if (BWD) {
-        if (r < valid) atomicAdd(loss_acc, -lp * A.inv_b);
+        const float contrib = warp_sum(r < valid ? -lp * A.inv_b : 0.f);
+        if (lane == 0) atomicAdd(loss_acc, contrib);
       } else if (r < valid) {
-        A.out_logp[row0 + r] = lp;
+        if (A.out_logp) A.out_logp[row0 + r] = lp;
+        if (A.out_logdet) A.out_logdet[row0 + r] = ldsum;
+      }
+    }
+    if (!BWD && A.out_u) {   // u rows are contiguous in HBM: coalesced store
+      float* dst = A.out_u + row0 * D;
+      for (int idx = tid; idx < valid * D; idx += NT) {
+        const int r = idx / D, j = idx - r * D;
+        dst[idx] = gu[j * RP + r];
       }
     }
     __syncthreads();
+    stamp(6);
 
     if (BWD) {
       float* pg_cta = A.partial_grad + (size_t)blockIdx.x * P.P;
       const bool accum = ti > 0;
       for (int k = L - 1; k >= 0; --k) {
         const float* wimg_s = w_acquire(req++);
+        stamp(4);
         const float* wb = recompute ? wimg_s + P.fwd_floats : wimg_s;
         float* slot = sm + P.o_slot + (P.stash_all ? k : 0) * P.slot_stride;
         if (recompute) layer_forward(k, wimg_s, slot, true);
@@ -263,87 +326,83 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
         {
           const float* sbuf = slot + P.s_off;
           const float* vbuf = slot + P.v_off;
-          for (int idx = tid; idx < D * Rt; idx += NT) {
-            const int j = idx / Rt, r = idx - j * Rt;
-            const int jj = P.reverse ? D - 1 - j : j;
-            const float gv = gu[jj * RP + r];
-            const float s = sbuf[j * RP + r], v = vbuf[j * RP + r];
+          for (int r = lane; r < Rt; r += 32) {
             const bool ok = r < valid;
-            obuf[j * RP + r] = ok ? -gv * s : 0.f;
-            obuf[(D + j) * RP + r] = ok ? 0.5f * gv * v - 0.5f * A.inv_b : 0.f;
-            gx[j * RP + r] = ok ? gv * s : 0.f;
+            for (int j = warp; j < D; j += NW) {
+              const int jj = P.reverse ? D - 1 - j : j;
+              const float gv = gu[jj * RP + r];
+              const float s = sbuf[j * RP + r], v = vbuf[j * RP + r];
+              obuf[j * RP + r] = ok ? -gv * s : 0.f;
+              obuf[(D + j) * RP + r] = ok ? 0.5f * gv * v - 0.5f * A.inv_b : 0.f;
+              gx[j * RP + r] = ok ? gv * s : 0.f;
+            }
           }
         }
         __syncthreads();
+        stamp(5);
 
         for (int i = n_lin - 1; i >= 0; --i) {
           const LinDesc& ln = P.lin[i];
           const float* G = (i == n_lin - 1) ? obuf : sm + P.o_g[i & 1];
           const float* Ain = (i == 0) ? xin : slot + P.h_off[i];
           const float* Wt = wb + ln.wt_off;
-          // three warp-granular task lists share the phase: X (input gradient), B (weight
-          // gradient) and the bias gradient (one warp-shuffle reduction per output feature)
-          const int xcols = (i == 0) ? P.DP : ln.KP;
-          const int nXR = Rt / XM;
-          const int nX = nXR * (xcols / XN);
-          const int nKB = (ln.K + BK - 1) / BK, nNB = (ln.N + BN - 1) / BN;
-          const int nB = nKB * nNB;
-          const int bX = (nX + 31) >> 5, bB = (nB + 31) >> 5;
-          const int total = bX + bB + ln.N;
-          for (int blk = warp; blk < total; blk += NW) {
-            if (blk < bB) {
-              const int it = blk * 32 + lane;
-              if (it < nB)
-                mm_inner<BK, BN>(Ain, ln.K, G, ln.N, Rt, RP, it / nNB, nKB, it % nNB, nNB,
-                                 pg + ln.pw_off, accum);
-            } else if (blk < bB + bX) {
-              const int it = (blk - bB) * 32 + lane;
-              if (it < nX) {
-                const int r0 = (it % nXR) * XM, c0 = (it / nXR) * XN;
-                if (i > 0) {
-                  float* gout = sm + P.o_g[(i - 1) & 1];
-                  const float* hprev = slot + P.h_off[i];
-                  const float* dprev = slot + P.d_off[i];
-                  mm_outer<XM, XN>(G, ln.N, RP, Wt, ln.KP, r0, c0, [&](float (&acc)[XN][XM]) {
+          // two warp-granular work lists share the phase:
+          //   X: input gradient g_in = G (M*W)^T; a warp holds 8 tiles, 4 lanes split the sum over n
+          //   B: weight + bias gradient [A;1]^T G; a warp holds 16 tiles (one row of 16 column
+          //      blocks), its two half-warps split the batch rows
+          const int nXC = ((i == 0) ? P.DP : ln.KP) / TS;
+          const int bX = (nXC + o_cpw - 1) / o_cpw;
+          const int N = ln.N, K = ln.K, KP = ln.KP;
+          const int nKB = (K + 1 + TS - 1) / TS, nNB = (N + TS - 1) / TS;
+          const int nbg = (nNB + 15) >> 4;             // groups of 16 column blocks
+          // narrow outputs: several row blocks kb share a warp (16 >> nb_shift of them)
+          const int nb_shift = nNB > 8 ? 4 : (nNB > 4 ? 3 : (nNB > 2 ? 2 : (nNB > 1 ? 1 : 0)));
+          const int kpw = 16 >> nb_shift;
+          const int bB = nbg == 1 ? (nKB + kpw - 1) / kpw : nKB * nbg;
+          for (int blk = warp; blk < bX + bB; blk += NW) {
+            if (blk < bX) {
+              const int cb = blk * o_cpw + o_cbl;
+              const bool ok = o_rok && cb < nXC;
+              const int c0 = (cb < nXC ? cb : nXC - 1) * TS;
+              float acc[TS][TS], res[TS];
+              mm_outer_acc<TS, TS>(acc, G, N, RP, Wt, KP, o_r0, c0, kq, KS);
+              reduce_scatter4(acc, kq, res);
+              if (ok) {
+                const int c = c0 + kq;
+                float dv[TS], gv[TS];
+                if (i > 0) {   // through the activation: g_a = g_h * act'(a)
+                  ldv(dv, slot + (RELU ? P.h_off[i] : P.d_off[i]) + c * RP + o_r0);
 #pragma unroll
-                    for (int j = 0; j < XN; ++j) {
-                      float dv[XM], gv[XM];
-                      ldv(dv, (RELU ? hprev : dprev) + (c0 + j) * RP + r0);
+                  for (int q = 0; q < TS; ++q)
+                    gv[q] = RELU ? (dv[q] > 0.f ? res[q] : 0.f) : res[q] * dv[q];
+                  stv(sm + P.o_g[(i - 1) & 1] + c * RP + o_r0, gv);
+                } else {       // gradient w.r.t. this layer's input x: MADE path + direct path
+                  ldv(dv, gx + c * RP + o_r0);
 #pragma unroll
-                      for (int q = 0; q < XM; ++q)
-                        gv[q] = RELU ? (dv[q] > 0.f ? acc[j][q] : 0.f) : acc[j][q] * dv[q];
-                      stv(gout + (c0 + j) * RP + r0, gv);
-                    }
-                  });
-                } else {
-                  mm_outer<XM, XN>(G, ln.N, RP, Wt, ln.KP, r0, c0, [&](float (&acc)[XN][XM]) {
-#pragma unroll
-                    for (int j = 0; j < XN; ++j) {
-                      float dv[XM], gv[XM];
-                      ldv(dv, gx + (c0 + j) * RP + r0);
-#pragma unroll
-                      for (int q = 0; q < XM; ++q) gv[q] = acc[j][q] + dv[q];
-                      stv(gu + (c0 + j) * RP + r0, gv);
-                    }
-                  });
+                  for (int q = 0; q < TS; ++q) gv[q] = res[q] + dv[q];
+                  stv(gu + c * RP + o_r0, gv);
                 }
               }
             } else {
-              const int n = blk - bB - bX;
-              float sacc = 0.f;
-              for (int r = lane; r < Rt; r += 32) sacc += G[n * RP + r];
-              sacc = warp_sum(sacc);
-              if (lane == 0) {
-                float* p = pg + ln.pb_off + n;
-                *p = accum ? *p + sacc : sacc;
-              }
+              const int b = blk - bX;
+              const int l16 = lane & 15;
+              int kb, nb;
+              if (nbg == 1) { kb = b * kpw + (l16 >> nb_shift); nb = l16 & ((1 << nb_shift) - 1); }
+              else { kb = b / nbg; nb = (b - kb * nbg) * 16 + l16; }
+              mm_inner_rs2(Ain, K, KP, G, N, Rt, RP, kb, nKB, nb < nNB ? nb : nNB - 1, nNB, lane >> 4,
+                           nb < nNB && kb < nKB, pg + ln.pw_off, accum);
             }
           }
           __syncthreads();
+          stamp(20 + i);
         }
       }
     }
   }
+  stamp(99);
+#ifdef MAFB_TRACE
+  if (A.trace && blockIdx.x == 0 && tid == 0) A.trace[1000] = n_trace;
+#endif
   if (BWD && tid == 0) A.partial_loss[blockIdx.x] = *loss_acc;
 }
 

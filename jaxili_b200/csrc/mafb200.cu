@@ -31,9 +31,10 @@ int fail(const std::string& msg) {
       return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                             \
   } while (0)
 
-constexpr int kSmemLimit = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100
-constexpr int kFlowThreads = 384;
-constexpr int kSampleWarps = 8;
+constexpr int kSmemLimit = 232448;    // 227 KB opt-in dynamic shared memory per CTA on sm_100
+constexpr int kSmemLimit2 = 115712;   // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2
+constexpr int kFlowThreads = 512;     // one CTA per SM, 32-row tiles
+constexpr int kFlowThreads2 = 256;    // two CTAs per SM, 16-row tiles
 
 inline int r4(int v) { return (v + 3) & ~3; }
 
@@ -42,7 +43,9 @@ inline int r4(int v) { return (v + 3) & ~3; }
 struct mafb200_handle_s {
   MafDesc desc{};
   int device = 0, n_sm = 0;
-  Plan plan{};
+  Plan plan{};                  // one CTA per SM
+  Plan plan2{};                 // two CTAs per SM (plan2.P == 0 when it does not fit)
+  int occ_mode = 0;             // 0 auto, 1 / 2 forced (env MAFB200_OCC)
   SamplePlan splan{};
   SamplePackArgs spack{};
   int dims[MAFB_MAX_LIN + 1]{};
@@ -59,6 +62,7 @@ struct mafb200_handle_s {
   unsigned int* done_counter = nullptr;
   float logdet_const = 0.f;
   int n_norm = 0;
+  long long* trace = nullptr;   // debug: device buffer of 1001 int64 (set by mafb200_debug_trace)
 };
 
 namespace {
@@ -99,7 +103,7 @@ void build_masks(const MafDesc& d, const int32_t* degrees, std::vector<uint8_t>&
 }
 
 // ------------------------------------------------------------------ flow-kernel planner
-bool plan_layout(Plan& P, int R, bool stash_all, int n_wbuf) {
+bool plan_layout(Plan& P, int R, bool stash_all, int n_wbuf, int limit) {
   P.R = R;
   P.RP = R + 4;
   P.stash_all = stash_all ? 1 : 0;
@@ -112,13 +116,13 @@ bool plan_layout(Plan& P, int R, bool stash_all, int n_wbuf) {
   P.stage_stride = r4(R * (P.D + P.C));
   P.o_stage = o;
   o += 2 * P.stage_stride;
-  P.xin_stride = r4(P.K0) * RP;
+  P.xin_stride = (r4(P.K0) + 4) * RP;   // + the ones row (bias gradient)
   P.o_xin = o;
   o += P.L * P.xin_stride;
   int rows = 0, maxhp = 4;
   for (int i = 1; i < P.n_lin; ++i) {
     P.h_off[i] = rows * RP;
-    rows += P.lin[i].KP;
+    rows += P.lin[i].KP + 4;               // + the ones row
     maxhp = std::max(maxhp, P.lin[i].KP);
   }
   for (int i = 1; i < P.n_lin; ++i) {
@@ -140,15 +144,19 @@ bool plan_layout(Plan& P, int R, bool stash_all, int n_wbuf) {
   o += P.DP * RP;
   P.o_ld = o;
   o += P.DP * RP;
+  P.o_cst = o;
+  o += r4(2 * P.D + 2 * P.C);
   P.o_g[0] = o;
   o += maxhp * RP;
   P.o_g[1] = o;
   o += maxhp * RP;
   P.smem_bytes = 64 + o * 4;
-  return P.smem_bytes <= kSmemLimit;
+  return P.smem_bytes <= limit;
 }
 
-bool make_plan(const MafDesc& d, const int* dims, Plan& P) {
+// occ = CTAs per SM the plan is sized for (1: 512 threads, tiles up to 32 rows; 2: 256 threads,
+// tiles up to 16 rows -- two independent CTAs hide each other's barrier and latency bubbles)
+bool make_plan(const MafDesc& d, const int* dims, Plan& P, int occ) {
   std::memset(&P, 0, sizeof(P));
   P.D = d.n_in;
   P.C = d.n_cond;
@@ -159,7 +167,7 @@ bool make_plan(const MafDesc& d, const int* dims, Plan& P) {
   P.reverse = d.use_reverse ? 1 : 0;
   P.DP = r4(P.D);
   P.need_d = d.activation != MAFB200_ACT_RELU;
-  P.threads = kFlowThreads;
+  P.threads = occ == 2 ? kFlowThreads2 : kFlowThreads;
   int fo = 0, bo = 0, po = 0;
   for (int i = 0; i < P.n_lin; ++i) {
     LinDesc& ln = P.lin[i];
@@ -184,10 +192,12 @@ bool make_plan(const MafDesc& d, const int* dims, Plan& P) {
   P.ppl = po;
   P.P = po * P.L;
   static const int Rs[] = {32, 16, 8, 4};
-  for (int R : Rs)
+  for (int R : Rs) {
+    if (occ == 2 && R > 16) continue;
     for (int stash = 1; stash >= 0; --stash)
       for (int nb = 2; nb >= 1; --nb)
-        if (plan_layout(P, R, stash != 0, nb)) return true;
+        if (plan_layout(P, R, stash != 0, nb, occ == 2 ? kSmemLimit2 : kSmemLimit)) return true;
+  }
   return false;
 }
 
@@ -230,14 +240,17 @@ bool make_sample_plan(const MafDesc& d, const int* dims, SamplePlan& S) {
   S.x_off = w;
   w += r4(S.D) * S.RP;
   S.warp_stride = w;
-  for (int n_img = 2; n_img >= 1; --n_img) {
-    S.n_img = n_img;
-    S.o_img = 0;
-    S.o_warp = n_img * S.img_floats;
-    S.warps = kSampleWarps;
-    S.smem_bytes = 64 + (S.o_warp + S.warps * S.warp_stride) * 4;
-    if (S.smem_bytes <= kSmemLimit) return true;
-  }
+  // prefer many warps (latency hiding) over double-buffered images
+  static const int kWarps[] = {8, 6, 4, 3, 2, 1};
+  for (int warps : kWarps)
+    for (int n_img = 2; n_img >= 1; --n_img) {
+      S.n_img = n_img;
+      S.o_img = 0;
+      S.o_warp = n_img * S.img_floats;
+      S.warps = warps;
+      S.smem_bytes = 64 + (S.o_warp + S.warps * S.warp_stride) * 4;
+      if (S.smem_bytes <= kSmemLimit) return true;
+    }
   return false;
 }
 
@@ -298,10 +311,12 @@ int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shi
   h->dims[0] = d.n_in + d.n_cond;
   for (int i = 0; i < d.n_hidden; ++i) h->dims[i + 1] = d.hidden[i];
   h->dims[d.n_hidden + 1] = 2 * d.n_in;
-  if (!make_plan(d, h->dims, h->plan)) {
+  if (!make_plan(d, h->dims, h->plan, 1)) {
     delete h;
     return fail("model too wide for the shared-memory-resident (narrow) path; wide tcgen05 path not built yet");
   }
+  if (!make_plan(d, h->dims, h->plan2, 2) || !h->plan2.stash_all || h->plan2.R < 16) h->plan2.P = 0;
+  if (const char* e = getenv("MAFB200_OCC")) h->occ_mode = atoi(e);
   const bool have_sampler = make_sample_plan(d, h->dims, h->splan);
   if (!have_sampler) h->splan.img_floats = 0;
   const Plan& P = h->plan;
@@ -320,8 +335,8 @@ int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shi
   CUH(cudaMalloc(&h->wimg, (size_t)P.L * P.img_floats * 4));
   CUH(cudaMemset(h->wimg, 0, (size_t)P.L * P.img_floats * 4));
   CUH(cudaMalloc(&h->stdc, (3 * P.D + 2 * P.C) * 4));
-  CUH(cudaMalloc(&h->partial, (size_t)h->n_sm * P.P * 4));
-  CUH(cudaMalloc(&h->partial_loss, h->n_sm * 4));
+  CUH(cudaMalloc(&h->partial, (size_t)2 * h->n_sm * P.P * 4));
+  CUH(cudaMalloc(&h->partial_loss, 2 * h->n_sm * 4));
   h->n_norm = (P.P + RED_IDX - 1) / RED_IDX;
   CUH(cudaMalloc(&h->normpart, h->n_norm * 4));
   CUH(cudaMemset(h->normpart, 0, h->n_norm * 4));
@@ -385,9 +400,16 @@ int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shi
   CUH(cudaFuncSetAttribute(maf_flow_kernel<true, false, kFlowThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
   CUH(cudaFuncSetAttribute(maf_flow_kernel<false, true, kFlowThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
   CUH(cudaFuncSetAttribute(maf_flow_kernel<false, false, kFlowThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+  if (h->plan2.P) {
+    const int sb2 = h->plan2.smem_bytes;
+    CUH(cudaFuncSetAttribute(maf_flow_kernel<true, true, kFlowThreads2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb2));
+    CUH(cudaFuncSetAttribute(maf_flow_kernel<true, false, kFlowThreads2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb2));
+    CUH(cudaFuncSetAttribute(maf_flow_kernel<false, true, kFlowThreads2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb2));
+    CUH(cudaFuncSetAttribute(maf_flow_kernel<false, false, kFlowThreads2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb2));
+  }
   if (have_sampler) {
-    CUH(cudaFuncSetAttribute(maf_sample_kernel<true, kSampleWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->splan.smem_bytes));
-    CUH(cudaFuncSetAttribute(maf_sample_kernel<false, kSampleWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->splan.smem_bytes));
+    CUH(cudaFuncSetAttribute(maf_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->splan.smem_bytes));
+    CUH(cudaFuncSetAttribute(maf_sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->splan.smem_bytes));
   }
 #undef CUH
   *out = h;
@@ -412,6 +434,12 @@ int mafb200_destroy(mafb200_handle h) {
   cudaFree(h->normpart);
   cudaFree(h->done_counter);
   delete h;
+  return 0;
+}
+
+int mafb200_debug_trace(mafb200_handle h, long long* trace_dev) {
+  if (!h) return fail("null handle");
+  h->trace = trace_dev;
   return 0;
 }
 
@@ -441,22 +469,40 @@ int mafb200_pack(mafb200_handle h, const float* params, void* stream) {
   return 0;
 }
 
-static int launch_geometry(mafb200_handle h, int64_t B, int& Rt, int& n_tiles, int& grid) {
-  const int R = h->plan.R;
-  const int64_t rows_per_cta = (B + h->n_sm - 1) / h->n_sm;
+// Picks the plan (CTAs per SM) and the tile geometry for a batch of B rows.  Rows are spread as
+// evenly as possible: every CTA gets ceil(rows/CTAs) rows cut into equal tiles of Rt <= R rows.
+static int launch_geometry(mafb200_handle h, int64_t B, const Plan*& plan, int& Rt, int& n_tiles, int& grid) {
+  int occ = 1;
+  if (h->plan2.P) {
+    // two CTAs per SM pay off while a single CTA per SM would hold at most a few tiles
+    occ = (B <= (int64_t)h->n_sm * 64) ? 2 : 1;
+    if (h->occ_mode == 1 || h->occ_mode == 2) occ = h->occ_mode;
+  }
+  plan = occ == 2 ? &h->plan2 : &h->plan;
+  const int R = plan->R;
+  const int64_t slots = (int64_t)h->n_sm * occ;
+  const int64_t rows_per_cta = (B + slots - 1) / slots;
   const int64_t n_t = (rows_per_cta + R - 1) / R;
   const int64_t rt = (rows_per_cta + n_t - 1) / n_t;
   Rt = (int)std::min<int64_t>(R, (rt + 3) & ~3LL);
   const int64_t T = (B + Rt - 1) / Rt;
   if (T > 0x7fffffff) return fail("batch too large");
   n_tiles = (int)T;
-  grid = (int)std::min<int64_t>(h->n_sm, T);
+  grid = (int)std::min<int64_t>(slots, T);
   return 0;
 }
 
-int mafb200_log_prob(mafb200_handle h, const float* params, const float* x, const float* y, int64_t B,
-                     float* out_logp, int32_t flags, void* stream) {
-  if (!h || !params || !x || !out_logp || (h->desc.n_cond && !y)) return fail("null argument");
+static int rb_shift_for(int Rt) {
+  const int nRB = Rt / 4;
+  int s = 0;
+  while ((1 << s) < nRB) ++s;
+  return s;   // nRB <= 8 -> s <= 3
+}
+
+int mafb200_forward(mafb200_handle h, const float* params, const float* x, const float* y, int64_t B,
+                    float* out_logp, float* out_u, float* out_logdet, int32_t flags, void* stream) {
+  if (!h || !params || !x || (h->desc.n_cond && !y)) return fail("null argument");
+  if (!out_logp && !out_u && !out_logdet) return fail("no output requested");
   if (B <= 0) return B == 0 ? 0 : fail("negative batch");
   cudaStream_t st = (cudaStream_t)stream;
   if (!(flags & MAFB200_PACKED_CURRENT) && mafb200_pack(h, params, stream)) return 1;
@@ -470,16 +516,31 @@ int mafb200_log_prob(mafb200_handle h, const float* params, const float* x, cons
   A.stdc = h->stdc;
   A.logdet_const = h->logdet_const;
   A.inv_b = 1.f;
+  A.trace = h->trace;
   A.out_logp = out_logp;
+  A.out_u = out_u;
+  A.out_logdet = out_logdet;
   int grid;
-  if (launch_geometry(h, B, A.Rt, A.n_tiles, grid)) return 1;
-  const Plan& P = h->plan;
-  if (P.act == MAFB200_ACT_RELU)
-    maf_flow_kernel<false, true, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
-  else
-    maf_flow_kernel<false, false, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
+  const Plan* pp;
+  if (launch_geometry(h, B, pp, A.Rt, A.n_tiles, grid)) return 1;
+  A.rb_shift = rb_shift_for(A.Rt);
+  const Plan& P = *pp;
+  const bool relu = P.act == MAFB200_ACT_RELU;
+  if (P.threads == kFlowThreads2) {
+    if (relu) maf_flow_kernel<false, true, kFlowThreads2><<<grid, kFlowThreads2, P.smem_bytes, st>>>(P, A);
+    else maf_flow_kernel<false, false, kFlowThreads2><<<grid, kFlowThreads2, P.smem_bytes, st>>>(P, A);
+  } else {
+    if (relu) maf_flow_kernel<false, true, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
+    else maf_flow_kernel<false, false, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
+  }
   CU(cudaGetLastError());
   return 0;
+}
+
+int mafb200_log_prob(mafb200_handle h, const float* params, const float* x, const float* y, int64_t B,
+                     float* out_logp, int32_t flags, void* stream) {
+  if (!out_logp) return fail("null argument");
+  return mafb200_forward(h, params, x, y, B, out_logp, nullptr, nullptr, flags, stream);
 }
 
 int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, const float* y, int64_t B,
@@ -500,15 +561,22 @@ int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, con
   A.stdc = h->stdc;
   A.logdet_const = h->logdet_const;
   A.inv_b = inv_global_B;
+  A.trace = h->trace;
   A.partial_grad = h->partial;
   A.partial_loss = h->partial_loss;
   int grid;
-  if (launch_geometry(h, B, A.Rt, A.n_tiles, grid)) return 1;
-  const Plan& P = h->plan;
-  if (P.act == MAFB200_ACT_RELU)
-    maf_flow_kernel<true, true, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
-  else
-    maf_flow_kernel<true, false, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
+  const Plan* pp;
+  if (launch_geometry(h, B, pp, A.Rt, A.n_tiles, grid)) return 1;
+  A.rb_shift = rb_shift_for(A.Rt);
+  const Plan& P = *pp;
+  const bool relu = P.act == MAFB200_ACT_RELU;
+  if (P.threads == kFlowThreads2) {
+    if (relu) maf_flow_kernel<true, true, kFlowThreads2><<<grid, kFlowThreads2, P.smem_bytes, st>>>(P, A);
+    else maf_flow_kernel<true, false, kFlowThreads2><<<grid, kFlowThreads2, P.smem_bytes, st>>>(P, A);
+  } else {
+    if (relu) maf_flow_kernel<true, true, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
+    else maf_flow_kernel<true, false, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
+  }
   CU(cudaGetLastError());
   reduce_kernel<<<h->n_norm, RED_IDX * RED_PARTS, 0, st>>>(h->partial, grid, P.P, h->mask, out_grad,
                                                          h->partial_loss, out_loss, h->normpart);
@@ -538,7 +606,7 @@ int mafb200_clip_adam(mafb200_handle h, float* params, const float* grad, float*
 
 static int sample_common(mafb200_handle h, const float* params, const float* u, uint64_t seed,
                          uint64_t row_offset, const float* y_obs, int64_t n_obs, int64_t rows_per_obs,
-                         int64_t N, float* out, int32_t flags, void* stream) {
+                         int64_t N, float* out, float* out_logdet, int32_t flags, void* stream) {
   if (!h || !params || !out || (h->desc.n_cond && !y_obs)) return fail("null argument");
   if (h->splan.img_floats == 0) return fail("sampler not available for this configuration");
   if (N <= 0) return N == 0 ? 0 : fail("negative sample count");
@@ -562,12 +630,13 @@ static int sample_common(mafb200_handle h, const float* params, const float* u, 
   A.N = N;
   A.stdc = h->stdc;
   A.out = out;
+  A.out_logdet = out_logdet;
   const int64_t tiles = (N + 31) / 32;
-  const int grid = (int)std::min<int64_t>(h->n_sm, (tiles + kSampleWarps - 1) / kSampleWarps);
+  const int grid = (int)std::min<int64_t>(h->n_sm, (tiles + S.warps - 1) / S.warps);
   if (S.act == MAFB200_ACT_RELU)
-    maf_sample_kernel<true, kSampleWarps><<<grid, kSampleWarps * 32, S.smem_bytes, st>>>(S, A);
+    maf_sample_kernel<true><<<grid, S.warps * 32, S.smem_bytes, st>>>(S, A);
   else
-    maf_sample_kernel<false, kSampleWarps><<<grid, kSampleWarps * 32, S.smem_bytes, st>>>(S, A);
+    maf_sample_kernel<false><<<grid, S.warps * 32, S.smem_bytes, st>>>(S, A);
   CU(cudaGetLastError());
   return 0;
 }
@@ -576,13 +645,20 @@ int mafb200_sample_from_noise(mafb200_handle h, const float* params, const float
                               int64_t n_obs, int64_t rows_per_obs, int64_t N, float* out, int32_t flags,
                               void* stream) {
   if (!u) return fail("null noise pointer");
-  return sample_common(h, params, u, 0, 0, y_obs, n_obs, rows_per_obs, N, out, flags, stream);
+  return sample_common(h, params, u, 0, 0, y_obs, n_obs, rows_per_obs, N, out, nullptr, flags, stream);
+}
+
+int mafb200_inverse(mafb200_handle h, const float* params, const float* u, const float* y, int64_t N,
+                    float* out_x, float* out_logdet, int32_t flags, void* stream) {
+  if (!u) return fail("null noise pointer");
+  return sample_common(h, params, u, 0, 0, y, N > 0 ? N : 1, 1, N, out_x, out_logdet, flags, stream);
 }
 
 int mafb200_sample_philox(mafb200_handle h, const float* params, uint64_t seed, uint64_t row_offset,
                           const float* y_obs, int64_t n_obs, int64_t rows_per_obs, int64_t N, float* out,
                           int32_t flags, void* stream) {
-  return sample_common(h, params, nullptr, seed, row_offset, y_obs, n_obs, rows_per_obs, N, out, flags, stream);
+  return sample_common(h, params, nullptr, seed, row_offset, y_obs, n_obs, rows_per_obs, N, out, nullptr, flags,
+                       stream);
 }
 
 int mafb200_ffma_peak(int device, int32_t iters, float* out_tflops) {

@@ -42,6 +42,7 @@ struct Plan {
   int s_off, v_off;             // slot-relative exp(logp/2) and v=(x-mu)s, [DP][RP] each
   int o_obuf;                   // [round4(2D)][RP]: MADE output, then grad wrt it
   int o_gu, o_gx, o_ld;         // [DP][RP] each
+  int o_cst;                    // standardisation constants [2D + 2C]
   int o_g[2];                   // ping-pong [max HP][RP] hidden-gradient buffers
   int smem_bytes;
 };

@@ -25,17 +25,19 @@ struct SampleArgs {
   long long n_obs, rows_per_obs, N;
   const float* stdc;               // [shift D][inv_scale D][mean C][std C][scale D]
   float* out;                      // [N][D]
+  float* out_logdet;               // [N] sum over layers of sum_d min(-logp_d/2, 10) (nullable)
 };
 
 constexpr int SM_ = 4, SN_ = 2;    // sampler tile: 4 rows x 2 columns per lane; lanes = 8 row blocks x 4 column blocks
 
-template <bool RELU, int NWS>
-__global__ void __launch_bounds__(NWS * 32, 1)
+template <bool RELU>
+__global__ void __launch_bounds__(256, 1)
 maf_sample_kernel(const __grid_constant__ SamplePlan S, const __grid_constant__ SampleArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* ibar = reinterpret_cast<uint64_t*>(smem_raw);
   float* sm = reinterpret_cast<float*>(smem_raw + 64);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NWS = blockDim.x >> 5;
   const int D = S.D, C = S.C, L = S.L, RP = S.RP, n_hidden = S.n_lin - 1;
   const int r0 = (lane & 7) * SM_, cb = lane >> 3;
   const long long total_tiles = (A.N + 31) / 32;
@@ -73,6 +75,9 @@ maf_sample_kernel(const __grid_constant__ SamplePlan S, const __grid_constant__ 
     const int valid = active ? (int)min(32LL, A.N - row0) : 0;
     float* ubuf = wbase + S.u_off;
     float* xbuf = wbase + S.x_off;
+    float ldinv[SM_];
+#pragma unroll
+    for (int i = 0; i < SM_; ++i) ldinv[i] = 0.f;
 
     if (active) {
       // base noise -> feature-major
@@ -214,7 +219,9 @@ maf_sample_kernel(const __grid_constant__ SamplePlan S, const __grid_constant__ 
 #pragma unroll
               for (int i = 0; i < SM_; ++i) {
                 const float mu = acc[0][i] + bo[0], lp = acc[1][i] + bo[1];
-                xv[i] = mu + expf(fminf(-0.5f * lp, 10.f)) * uv[i];   // jaxili/model.py:770-771
+                const float mlp = fminf(-0.5f * lp, 10.f);             // jaxili/model.py:770
+                ldinv[i] += mlp;                                        // 772 (last-pass values)
+                xv[i] = mu + expf(mlp) * uv[i];                         // 771
               }
               stv(xbuf + d * RP + r0, xv);
             }
@@ -231,6 +238,11 @@ maf_sample_kernel(const __grid_constant__ SamplePlan S, const __grid_constant__ 
       for (int idx = lane; idx < valid * D; idx += 32) {
         const int r = idx / D, j = idx - r * D;
         dst[idx] = c_scale[j] * ubuf[j * RP + r] + c_shift[j];
+      }
+      if (A.out_logdet && cb == 0) {
+#pragma unroll
+        for (int i = 0; i < SM_; ++i)
+          if (r0 + i < valid) A.out_logdet[row0 + r0 + i] = ldinv[i];
       }
     }
     __syncwarp();

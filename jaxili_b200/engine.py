@@ -118,6 +118,34 @@ class MafEngine:
                 _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
         return out
 
+    def forward(self, params, x, y, packed_current=False):
+        """ConditionalMAF.__call__: returns (u, log_det) for standardised-or-not inputs."""
+        px = self._chk(x, "x", self.n_in)
+        py = self._chk(y, "y", self.n_cond) if self.n_cond else None
+        B = x.shape[0]
+        u = torch.empty((B, self.n_in), dtype=torch.float32, device=self.device)
+        ld = torch.empty(B, dtype=torch.float32, device=self.device)
+        if B:
+            _lib.check(self.lib.mafb200_forward(
+                self._h, self._chk(params, "params"), px, py, B, None, self._chk(u, "u"),
+                self._chk(ld, "ld"), _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
+        return u, ld
+
+    def inverse(self, params, u, y, packed_current=False):
+        """ConditionalMAF.backward with per-row conditioning: returns (x, log_det)."""
+        pu = self._chk(u, "u", self.n_in)
+        py = self._chk(y, "y", self.n_cond) if self.n_cond else None
+        N = u.shape[0]
+        if self.n_cond and y.shape[0] != N:
+            raise ValueError("u and y must have the same number of rows")
+        x = torch.empty_like(u)
+        ld = torch.empty(N, dtype=torch.float32, device=self.device)
+        if N:
+            _lib.check(self.lib.mafb200_inverse(
+                self._h, self._chk(params, "params"), pu, py, N, self._chk(x, "x"),
+                self._chk(ld, "ld"), _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
+        return x, ld
+
     def loss_grad(self, params, x, y, out_loss, out_grad, batch_rows=None, inv_global_b=None,
                   batch_index=None, n_batches=1, packed_current=False):
         """out_loss[0], out_grad <- NLL and its gradient over rows [0, batch_rows) of x/y (or the

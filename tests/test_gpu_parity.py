@@ -128,9 +128,9 @@ def test_clip_adam_matches_oracle(kind):
                 st.count = tn
     assert step.item() == 6
     assert np.max(np.abs(p.cpu().numpy() - ref)) < 2e-5 * max(1.0, np.abs(ref).max())
-    # masked weights never move
-    mask0 = spec.flat_mask() == 0
-    assert (p.cpu().numpy()[mask0] == flat[mask0]).all()
+    if kind == "adam":  # masked weights never move (weight decay, as in optax, would move them)
+        mask0 = spec.flat_mask() == 0
+        assert (p.cpu().numpy()[mask0] == flat[mask0]).all()
 
 
 @pytest.mark.parametrize("name,N,rev,act", [("c2", 4096, True, "relu"), ("c1", 1000, True, "relu"),
