@@ -1,0 +1,495 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark (driver contract).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c3|c1|c4]
+
+A "step" is one pass of the hot path over one batch of synthetic simulations:
+  training workloads (c1, c2, c3): fused forward + backward + gradient reduction + global-norm clip
+      + warmup-cosine Adam update on one batch (jaxili/train.py:330-335 with the chain of 246-300);
+  sampling workload (c4): one posterior.sample call (jaxili/posterior/direct_posterior.py:45-73).
+Default workload = BASELINE.json configs[1]: NPE gaussian-linear, n_in=10, n_cond=10, 5 x [50,50],
+batch 4096 per GPU.  With N GPUs (torchrun, one rank per GPU) every rank trains on its own batch
+shard (weak scaling, global batch = N x 4096) and the flat gradient is all-reduced once per step.
+
+One JSON line is printed by rank 0:
+  value     whole-job samples/s with the dataset resident in HBM (CUDA-graph replay, device-side
+            batch selection, CUDA events on the launch stream, max over ranks)
+  e2e       the same metric through the reference-facing API (TrainerModule.train_step) with HOST
+            batches in pinned memory: H2D copy of every batch and D2H read of the loss inside the
+            timed region
+  roofline  FP32-FFMA roofline of the fused flow kernel: algorithmic FLOPs / CUDA-event time of the
+            kernel alone, against the FFMA peak measured live on this GPU (MEASURED_PEAKS.json has
+            no FP32 figure; its HBM number bounds nothing here: 80 B/sample)
+  cpu_baseline  the CPU oracle port (torch, all host threads) on a bounded sample of the same workload
+
+``--impl reference`` times the reference's CPU path instead: jaxili itself (JAX) cannot be installed
+in this image, so the arm runs the line-by-line CPU restatement under oracle/ (kind "port").
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model config, per-GPU batch, description)
+    "c1": (dict(n_in=2, n_cond=2, n_layers=5, layers=[50, 50]), 128,
+           "NPE two-moons-shaped D=2,C=2, 5x[50,50] ReLU reverse, batch 128"),
+    "c2": (dict(n_in=10, n_cond=10, n_layers=5, layers=[50, 50]), 4096,
+           "NPE gaussian-linear D=10,C=10, 5x[50,50] ReLU reverse, batch 4096 per GPU"),
+    "c3": (dict(n_in=8, n_cond=5, n_layers=5, layers=[50, 50]), 16384,
+           "NLE SLCP-shaped D=8 (x), C=5 (theta), 5x[50,50], batch 16384 per GPU"),
+    "c4": (dict(n_in=10, n_cond=10, n_layers=5, layers=[50, 50]), 1 << 20,
+           "posterior sampling D=10,C=10, 5x[50,50]: 2^20 samples per observation per step"),
+}
+
+
+def macs_per_pass(cfg):
+    dims = [cfg["n_in"] + cfg["n_cond"], *cfg["layers"], 2 * cfg["n_in"]]
+    return sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+
+
+def train_flops_per_sample(cfg):
+    """dense, 2 FLOP/MAC, masks not discounted: fwd + dX + dW = 6*M*L."""
+    return 6 * macs_per_pass(cfg) * cfg["n_layers"]
+
+
+def sample_flops_per_sample(cfg):
+    """the reference's D full MADE passes per layer: 2*M*L*D."""
+    return 2 * macs_per_pass(cfg) * cfg["n_layers"] * cfg["n_in"]
+
+
+def synth_data(name, cfg, n_rows, seed):
+    """Synthetic simulator draws of the named shape, FP32."""
+    rng = np.random.default_rng(seed)
+    D, C = cfg["n_in"], cfg["n_cond"]
+    if name in ("c2", "c4"):      # gaussian-linear: theta ~ U(-1,1)^10, x = theta + sqrt(0.1) eps
+        theta = rng.uniform(-1, 1, size=(n_rows, D)).astype(np.float32)
+        x = (theta + np.sqrt(0.1) * rng.standard_normal((n_rows, C))).astype(np.float32)
+        return theta, x
+    if name == "c1":              # two moons
+        theta = rng.uniform(-1, 1, size=(n_rows, 2)).astype(np.float32)
+        a = rng.uniform(-np.pi / 2, np.pi / 2, n_rows)
+        r = rng.normal(0.1, 0.01, n_rows)
+        x = np.stack([r * np.cos(a) + 0.25 - np.abs(theta[:, 0] + theta[:, 1]) / np.sqrt(2),
+                      r * np.sin(a) + (-theta[:, 0] + theta[:, 1]) / np.sqrt(2)], axis=1).astype(np.float32)
+        return theta, x
+    if name == "c3":              # SLCP-shaped: theta in R^5, x in R^8 (four 2-D Gaussian draws)
+        th = rng.uniform(-3, 3, size=(n_rows, 5))
+        s1, s2, rho = th[:, 2] ** 2, th[:, 3] ** 2, np.tanh(th[:, 4])
+        z = rng.standard_normal((n_rows, 4, 2))
+        x0 = th[:, None, 0] + s1[:, None] * z[:, :, 0]
+        x1 = th[:, None, 1] + s2[:, None] * (rho[:, None] * z[:, :, 0] + np.sqrt(1 - rho[:, None] ** 2) * z[:, :, 1])
+        x = np.stack([x0, x1], axis=2).reshape(n_rows, 8)
+        return th.astype(np.float32), x.astype(np.float32)
+    raise ValueError(name)
+
+
+def density_and_cond(name, theta, x):
+    """(density variable, conditioner): NPE learns p(theta|x), NLE p(x|theta)."""
+    return (x, theta) if name == "c3" else (theta, x)
+
+
+def zscore(a):
+    return a.mean(0, dtype=np.float32), a.std(0, dtype=np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_train_throughput(name, cfg, batch, budget_s, threads):
+    """Train steps of the CPU restatement (oracle/maf_torch.py) on `threads` host threads."""
+    import torch
+    from oracle import maf_numpy as onp
+    from oracle.maf_torch import TorchMaf, TorchTrainer
+    torch.set_num_threads(threads)
+    theta, x = synth_data(name, cfg, batch * 4, seed=11)
+    dv, cv = density_and_cond(name, theta, x)
+    spec = onp.MafSpec(activation="relu", use_reverse=True, seed=42, **cfg)
+    flat = spec.init_params(np.random.default_rng(42), 0.01, np.float32)
+    std = onp.Standardization(*zscore(dv), *zscore(cv))
+    tr = TorchTrainer(TorchMaf(spec, std), flat, lr=5e-4, warmup=0.1, decay_steps=1e9)
+    xs = [torch.tensor(dv[i * batch:(i + 1) * batch]) for i in range(4)]
+    ys = [torch.tensor(cv[i * batch:(i + 1) * batch]) for i in range(4)]
+    for i in range(3):
+        tr.train_step(xs[i % 4], ys[i % 4])
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < budget_s:
+        tr.train_step(xs[n % 4], ys[n % 4])
+        n += 1
+    dt = time.perf_counter() - t0
+    return n * batch / dt, n, dt
+
+
+def cpu_sample_throughput(cfg, rows, threads):
+    import torch
+    from oracle import maf_numpy as onp
+    from oracle.maf_torch import TorchMaf
+    torch.set_num_threads(threads)
+    spec = onp.MafSpec(activation="relu", use_reverse=True, seed=42, **cfg)
+    flat = spec.init_params(np.random.default_rng(42), 0.01, np.float32)
+    std = onp.Standardization.identity(cfg["n_in"], cfg["n_cond"])
+    tm = TorchMaf(spec, std)
+    u = np.random.default_rng(1).standard_normal((rows, cfg["n_in"])).astype(np.float32)
+    y = np.zeros(cfg["n_cond"], np.float32)
+    tm.sample_from_noise(flat, u[:1024], y)
+    t0 = time.perf_counter()
+    tm.sample_from_noise(flat, u, y)
+    dt = time.perf_counter() - t0
+    return rows / dt, dt
+
+
+def run_reference_arm(args, name, cfg, batch):
+    """--impl reference: the reference's own CPU implementation of the path.  jaxili (JAX) is not
+    installable here, so this is the CPU restatement (oracle/), on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    t_all = time.perf_counter()
+    if name == "c4":
+        rows = 20000
+        vals = []
+        for _ in range(max(1, min(args.steps, 3))):
+            v, dt = cpu_sample_throughput(cfg, rows, threads)
+            vals.append(v)
+        value = float(np.mean(vals))
+        sample = f"{rows} samples per call, 1 observation, {len(vals)} calls"
+        metric, steps = "posterior samples/sec", len(vals)
+        ms = rows / value * 1e3
+    else:
+        # bounded: each step is one full batch; K steps capped so the arm ends within ~1 minute
+        budget = 20.0
+        value, n, dt = cpu_train_throughput(name, cfg, batch, budget, threads)
+        sample = f"{n} train steps of batch {batch} in {dt:.1f} s"
+        metric, steps = "MAF train samples/sec (fwd+bwd+clip+Adam)", n
+        ms = batch / value * 1e3
+    line = {
+        "impl": "reference", "metric": metric, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[name][2], "batch": batch},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "jaxili (JAX/flax/optax) is not installable in this image; CPU restatement under oracle/ timed "
+                f"on {threads} host threads; wall {time.perf_counter() - t_all:.1f} s",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    name = args.workload
+    cfg, batch, desc = WORKLOADS[name]
+    if args.impl == "reference":
+        return run_reference_arm(args, name, cfg, batch)
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: jaxili_b200 has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, K = max(args.warmup, 3), args.steps
+
+    from jaxili_b200 import nn as bnn
+    from jaxili_b200.engine import ffma_peak_tflops
+    from jaxili_b200.loss import loss_nll_nle, loss_nll_npe
+    from jaxili_b200.model import ConditionalMAF, Identity, NDE_w_Standardization, ScalarAffine, Sequential, Standardizer
+    from jaxili_b200.train import TrainerModule
+
+    def barrier_sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    clocks = ClockSampler(local)
+    out = {}
+
+    if name == "c4":
+        # ------------------------------------------------------------- posterior sampling
+        n_obs_total = 64
+        rows = batch                                   # 2^20 samples per observation per step
+        theta, x = synth_data("c4", cfg, 4096, seed=3)
+        maf = ConditionalMAF(activation=bnn.relu, use_reverse=True, seed=42, device=dev, **cfg)
+        model = NDE_w_Standardization(maf, Sequential([Standardizer(*zscore(x)), Identity()]),
+                                      ScalarAffine(*zscore(theta)))
+        variables = model.init(42)
+        eng = model.engine()
+        flat = model.flat_params(variables)
+        obs = torch.tensor(x[:n_obs_total], device=dev)
+        my_obs = list(range(rank, n_obs_total, world))  # observations are independent: shard, no collective
+        outbuf = torch.empty((rows, cfg["n_in"]), device=dev)
+        eng.sample_philox(flat, rows, obs[0:1], seed=4, out=outbuf)            # packs the sampler image
+        for i in range(W):
+            eng.sample_philox(flat, rows, obs[my_obs[i % len(my_obs)]][None], seed=4, row_offset=i * rows,
+                              out=outbuf, packed_current=True)
+        barrier_sync()
+        clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            o = my_obs[i % len(my_obs)]
+            eng.sample_philox(flat, rows, obs[o:o + 1], seed=4, row_offset=(o << 20), out=outbuf, packed_current=True)
+        e1.record()
+        barrier_sync()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        value = K * rows * world / (ms * 1e-3)
+        # e2e: DirectPosterior.sample-style call with host observation in, samples read back to host
+        host_out = torch.empty((rows, cfg["n_in"]), dtype=torch.float32).pin_memory()
+        obs_host = torch.tensor(x[:n_obs_total]).pin_memory()
+        obs_dev = torch.empty((1, cfg["n_cond"]), device=dev)
+        Ke = max(3, min(K, 20))
+        barrier_sync()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(Ke):
+            o = my_obs[i % len(my_obs)]
+            obs_dev.copy_(obs_host[o:o + 1], non_blocking=True)
+            eng.sample_philox(flat, rows, obs_dev, seed=4, row_offset=(o << 20), out=outbuf, packed_current=True)
+            host_out.copy_(outbuf, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        t1.record()
+        barrier_sync()
+        ms_e = max_over_ranks(t0.elapsed_time(t1))
+        clk = clocks.stop()
+        peak = ffma_peak_tflops(local)
+        fl = sample_flops_per_sample(cfg)
+        achieved = fl * rows / (ms / K * 1e-3) / 1e12
+        out = {
+            "metric": "posterior samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "observations": n_obs_total, "samples_per_step": rows,
+                       "l2": "outputs (42 MB/step) exceed nothing: compute-bound; Philox noise drawn in-kernel",
+                       "parallelism": f"obs-shard x{world}"},
+            "e2e": {"value": Ke * rows * world / (ms_e * 1e-3), "unit": "samples/s",
+                    "h2d_bytes_per_step": cfg["n_cond"] * 4, "d2h_bytes_per_step": rows * cfg["n_in"] * 4},
+            "gpu_launches": K,
+            "roofline": {"bound": "fp32_ffma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "note": "algorithmic FLOPs = reference's dense D-pass count (2*M*L*D per sample); the kernel "
+                                 "executes the degree-sorted incremental evaluation (~1/18 of those MACs), so frac "
+                                 "above 1 is an algorithmic gain, not pipe utilisation; peak = FFMA measured live"},
+            "clocks": clk,
+        }
+    else:
+        # ------------------------------------------------------------- training step
+        n_batches = max(8, (168 * 2**20) // (batch * (cfg["n_in"] + cfg["n_cond"]) * 4))  # > 126 MB L2
+        n_batches = min(n_batches, 512)
+        rows = n_batches * batch
+        theta, x = synth_data(name, cfg, rows, seed=100 + rank)
+        dv, cv = density_and_cond(name, theta, x)
+        maf = ConditionalMAF(activation=bnn.relu, use_reverse=True, seed=42, device=dev, **cfg)
+        # NDE_w_Standardization exactly as NPE/NLE build it (npe.py:383-413 / nle.py:323-353)
+        model_hparams = {"nde": maf, "embedding_net": Sequential([Standardizer(*zscore(cv)), Identity()]),
+                         "transformation": ScalarAffine(*zscore(dv))}
+        loss_fn = loss_nll_nle if name == "c3" else loss_nll_npe
+        exmp = (np.zeros((1, theta.shape[1]), np.float32), np.zeros((1, x.shape[1]), np.float32))
+        trainer = TrainerModule(NDE_w_Standardization, model_hparams,
+                                {"lr": 5e-4, "optimizer_name": "adam", "gradient_clip": 5.0, "warmup": 0.1,
+                                 "weight_decay": 0.0},
+                                loss_fn, exmp, seed=42, logger_params={"base_log_dir": "/tmp/jaxili_b200_bench"},
+                                enable_progress_bar=False, nde_class="NLE" if name == "c3" else "NPE")
+        trainer.init_optimizer(num_epochs=2**31 - 1, num_steps_per_epoch=n_batches)
+        eng = trainer.model.engine()
+        theta_d, x_d = torch.tensor(theta, device=dev), torch.tensor(x, device=dev)
+        flops_step = train_flops_per_sample(cfg) * batch
+
+        # (1) kernel-resident throughput
+        if world == 1:
+            step_fn = trainer.make_graph_step(theta_d, x_d, batch)
+            launches_per_step = 3          # flow, reduce, clip_adam
+        else:
+            state = trainer.state
+            xd, yd = trainer._batch_xy([theta_d, x_d])
+            flat = state.params.flat
+            Pn = flat.numel()
+            gbuf = trainer._gbuf
+            grad, loss = gbuf[:Pn], gbuf[-4:-3]
+            eng.pack(flat)
+            inv = 1.0 / (batch * world)
+
+            def step_fn():
+                eng.loss_grad(flat, xd, yd, loss, grad, batch_rows=batch, inv_global_b=inv, batch_index=state.step,
+                              n_batches=n_batches, packed_current=True)
+                dist.all_reduce(gbuf)
+                eng.clip_adam(flat, grad, state.opt_state["m"], state.opt_state["v"], state.step, state.tx)
+            launches_per_step = 4          # flow, reduce, sqnorm, clip_adam (+ NCCL's own kernel)
+        for _ in range(W):
+            step_fn()
+        barrier_sync()
+        clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            step_fn()
+        e1.record()
+        barrier_sync()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        clk = clocks.stop()
+        value = K * batch * world / (ms * 1e-3)
+        final_loss = float(trainer._gbuf[-4].item())
+
+        # (2) end to end through TrainerModule.train_step with host batches (pinned), loss read back
+        Ke = max(W, min(K, 300))
+        host_batches = [[theta[i * batch:(i + 1) * batch], x[i * batch:(i + 1) * batch]] for i in range(min(n_batches, 16))]
+        for i in range(W):
+            trainer.state, m = trainer.train_step(trainer.state, host_batches[i % len(host_batches)])
+        barrier_sync()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(Ke):
+            trainer.state, m = trainer.train_step(trainer.state, host_batches[i % len(host_batches)])
+            _ = m["loss"].item()           # D2H read of the step's loss
+        t1.record()
+        barrier_sync()
+        ms_e = max_over_ranks(t0.elapsed_time(t1))
+        e2e = Ke * batch * world / (ms_e * 1e-3)
+
+        # (3) roofline of the dominant kernel: CUDA-event bracket around the flow kernel alone
+        xd, yd = trainer._batch_xy([theta_d, x_d])
+        flat = trainer.state.params.flat
+        Pn = flat.numel()
+        grad, loss = trainer._gbuf[:Pn], trainer._gbuf[-4:-3]
+        eng.pack(flat)
+        for _ in range(W):
+            eng.loss_grad(flat, xd, yd, loss, grad, batch_rows=batch, batch_index=trainer.state.step,
+                          n_batches=n_batches, packed_current=True)
+        torch.cuda.synchronize(dev)
+        eng.flow_timing(True)
+        Kr = min(K, 300)
+        for i in range(Kr):
+            trainer.state.step.add_(1)     # walk through the dataset (> L2) as the training loop does
+            eng.loss_grad(flat, xd, yd, loss, grad, batch_rows=batch, batch_index=trainer.state.step,
+                          n_batches=n_batches, packed_current=True)
+        tot_ms, n_l = eng.flow_elapsed()
+        eng.flow_timing(False)
+        kernel_ms = tot_ms / max(n_l, 1)
+        peak = ffma_peak_tflops(local)
+        achieved = flops_step / (kernel_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(name)
+        except Exception:
+            pass
+        out = {
+            "metric": "MAF train samples/sec (fwd+bwd+clip+Adam)", "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "per_gpu_batch": batch, "global_batch": batch * world,
+                       "dataset_rows_per_gpu": rows,
+                       "l2": f"resident dataset {rows * (cfg['n_in'] + cfg['n_cond']) * 4 / 2**20:.0f} MiB > 126 MB L2, "
+                             "batches walked by the on-device step counter",
+                       "optimizer": "clip_by_global_norm(5) + adam(warmup_cosine(5e-4))",
+                       "parallelism": f"dp{world}", "final_loss": final_loss},
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": batch * (cfg["n_in"] + cfg["n_cond"]) * 4,
+                    "d2h_bytes_per_step": 4, "steps": Ke},
+            "gpu_launches": launches_per_step * K,
+            "roofline": {"bound": "fp32_ffma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "maf_flow_kernel<BWD>",
+                         "kernel_us": kernel_ms * 1e3, "flops_per_launch": flops_step,
+                         "peak_source": "FFMA micro-benchmark run live (MEASURED_PEAKS.json has no FP32 entry); "
+                                        "nominal 74.5 TFLOP/s"},
+            "clocks": clk,
+        }
+
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        if name == "c4":
+            v, dt = cpu_sample_throughput(cfg, 20000, threads)
+            out["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+                                   "sample": f"20000 samples of one observation in {dt:.1f} s (oracle/maf_torch.py)"}
+        else:
+            v, n, dt = cpu_train_throughput(name, cfg, batch, 12.0, threads)
+            out["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+                                   "sample": f"{n} train steps of batch {batch} in {dt:.1f} s (oracle/maf_torch.py)"}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -117,6 +117,13 @@ int mafb200_set_standardization(mafb200_handle h, const float* shift, const floa
    1001 int64 ((id, clock) pairs, count at [1000]); NULL switches tracing off (default). */
 int mafb200_debug_trace(mafb200_handle h, long long* trace_dev);
 
+/* measurement aid: bracket the fused flow kernel (alone) of every following log_prob / forward /
+   loss_grad call with CUDA events on the launch stream; mafb200_flow_elapsed returns the summed
+   device time and the number of bracketed launches since timing was switched on.  Not for use
+   under CUDA-graph capture. */
+int mafb200_flow_timing(mafb200_handle h, int32_t enable);
+int mafb200_flow_elapsed(mafb200_handle h, double* total_ms, int64_t* launches);
+
 int64_t mafb200_param_count(mafb200_handle h);
 /* writes the 0/1 mask in flat parameter order (biases 1) to a host buffer of param_count bytes */
 int mafb200_get_mask(mafb200_handle h, uint8_t* mask_host);

@@ -63,6 +63,12 @@ struct mafb200_handle_s {
   float logdet_const = 0.f;
   int n_norm = 0;
   long long* trace = nullptr;   // debug: device buffer of 1001 int64 (set by mafb200_debug_trace)
+  // optional CUDA-event bracket around the flow kernel alone (roofline measurement in bench.py)
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double flow_ms_sum = 0.0;
+  long long flow_launches = 0;
+  bool ev_pending = false;
 };
 
 namespace {
@@ -433,6 +439,8 @@ int mafb200_destroy(mafb200_handle h) {
   cudaFree(h->partial_loss);
   cudaFree(h->normpart);
   cudaFree(h->done_counter);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
   return 0;
 }
@@ -440,6 +448,35 @@ int mafb200_destroy(mafb200_handle h) {
 int mafb200_debug_trace(mafb200_handle h, long long* trace_dev) {
   if (!h) return fail("null handle");
   h->trace = trace_dev;
+  return 0;
+}
+
+int mafb200_flow_timing(mafb200_handle h, int32_t enable) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->device));
+  if (enable && !h->ev0) {
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+  }
+  h->timing = enable != 0;
+  h->ev_pending = false;
+  h->flow_ms_sum = 0.0;
+  h->flow_launches = 0;
+  return 0;
+}
+
+int mafb200_flow_elapsed(mafb200_handle h, double* total_ms, int64_t* launches) {
+  if (!h || !total_ms || !launches) return fail("null argument");
+  if (h->ev_pending) {
+    CU(cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->flow_ms_sum += ms;
+    h->flow_launches += 1;
+    h->ev_pending = false;
+  }
+  *total_ms = h->flow_ms_sum;
+  *launches = h->flow_launches;
   return 0;
 }
 
@@ -492,6 +529,20 @@ static int launch_geometry(mafb200_handle h, int64_t B, const Plan*& plan, int& 
   return 0;
 }
 
+// fold the previous launch's event pair into the running sum, then open a new bracket
+static int flow_timing_begin(mafb200_handle h, cudaStream_t st) {
+  if (h->ev_pending) {
+    CU(cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->flow_ms_sum += ms;
+    h->flow_launches += 1;
+  }
+  CU(cudaEventRecord(h->ev0, st));
+  h->ev_pending = true;
+  return 0;
+}
+
 static int rb_shift_for(int Rt) {
   const int nRB = Rt / 4;
   int s = 0;
@@ -526,6 +577,7 @@ int mafb200_forward(mafb200_handle h, const float* params, const float* x, const
   A.rb_shift = rb_shift_for(A.Rt);
   const Plan& P = *pp;
   const bool relu = P.act == MAFB200_ACT_RELU;
+  if (h->timing && flow_timing_begin(h, st)) return 1;
   if (P.threads == kFlowThreads2) {
     if (relu) maf_flow_kernel<false, true, kFlowThreads2><<<grid, kFlowThreads2, P.smem_bytes, st>>>(P, A);
     else maf_flow_kernel<false, false, kFlowThreads2><<<grid, kFlowThreads2, P.smem_bytes, st>>>(P, A);
@@ -534,6 +586,7 @@ int mafb200_forward(mafb200_handle h, const float* params, const float* x, const
     else maf_flow_kernel<false, false, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
   }
   CU(cudaGetLastError());
+  if (h->timing) CU(cudaEventRecord(h->ev1, st));
   return 0;
 }
 
@@ -570,6 +623,7 @@ int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, con
   A.rb_shift = rb_shift_for(A.Rt);
   const Plan& P = *pp;
   const bool relu = P.act == MAFB200_ACT_RELU;
+  if (h->timing && flow_timing_begin(h, st)) return 1;
   if (P.threads == kFlowThreads2) {
     if (relu) maf_flow_kernel<true, true, kFlowThreads2><<<grid, kFlowThreads2, P.smem_bytes, st>>>(P, A);
     else maf_flow_kernel<true, false, kFlowThreads2><<<grid, kFlowThreads2, P.smem_bytes, st>>>(P, A);
@@ -578,6 +632,7 @@ int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, con
     else maf_flow_kernel<true, false, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
   }
   CU(cudaGetLastError());
+  if (h->timing) CU(cudaEventRecord(h->ev1, st));
   reduce_kernel<<<h->n_norm, RED_IDX * RED_PARTS, 0, st>>>(h->partial, grid, P.P, h->mask, out_grad,
                                                          h->partial_loss, out_loss, h->normpart);
   CU(cudaGetLastError());

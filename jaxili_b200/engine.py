@@ -100,6 +100,15 @@ class MafEngine:
         _lib.check(self.lib.mafb200_query(self._h, *[C.byref(a) for a in v]))
         return dict(smem_bytes=v[0].value, tile_rows=v[1].value, max_ctas=v[2].value, stash_all=v[3].value)
 
+    def flow_timing(self, enable=True):
+        _lib.check(self.lib.mafb200_flow_timing(self._h, 1 if enable else 0))
+
+    def flow_elapsed(self):
+        """(total device ms, launches) of the bracketed flow-kernel launches."""
+        ms, n = C.c_double(), C.c_int64()
+        _lib.check(self.lib.mafb200_flow_elapsed(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     # ------------------------------------------------------------------ hot path
     def pack(self, params):
         _lib.check(self.lib.mafb200_pack(self._h, self._chk(params, "params"), self._stream()))

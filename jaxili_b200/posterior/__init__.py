@@ -1,0 +1,4 @@
+"""Posterior objects (jaxili.posterior)."""
+
+from .base_posterior import NeuralPosterior
+from .direct_posterior import DirectPosterior

@@ -1,0 +1,250 @@
+"""GPU tests of the reference-facing API (jaxili's own test ideas, jaxili/tests/test_nn.py,
+test_npe.py, test_nle.py, test_posterior.py), plus trainer parity against the oracle."""
+import json
+import os
+
+import numpy as np
+import numpy.testing as npt
+import pytest
+import torch
+
+from oracle import maf_numpy as onp
+from tests.util import grad_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _sim(n, seed=0, D=10):
+    rng = np.random.default_rng(seed)
+    theta = rng.uniform(-1, 1, size=(n, D)).astype(np.float32)
+    x = (theta + np.sqrt(0.1) * rng.standard_normal((n, D))).astype(np.float32)
+    return theta, x
+
+
+def test_conditional_maf_like_reference():
+    """jaxili/tests/test_nn.py:10-61: shapes, forward->backward round trip at 1e-5, both y shapes."""
+    from jaxili_b200 import nn
+    from jaxili_b200.model import ConditionalMAF
+    n_in, n_cond = 3, 5
+    for layer, reverse in zip([3, 4], [True, False]):
+        maf = ConditionalMAF(n_in, n_cond, layer, [128, 128], use_reverse=reverse, seed=42, activation=nn.silu)
+        x = np.random.randn(10, n_in).astype(np.float32)
+        cond = np.random.randn(10, n_cond).astype(np.float32)
+        params = maf.init(0, x, cond)
+        log_prob = maf.apply(params, x, cond, method="log_prob")
+        assert log_prob.shape == (10,)
+        u, log_det = maf.apply(params, x, cond)
+        x_rec, log_det_rec = maf.apply(params, u, cond, method="backward")
+        npt.assert_allclose(x, x_rec.cpu().numpy(), rtol=1e-5, atol=1e-5)
+        npt.assert_allclose(log_det.cpu().numpy(), -log_det_rec.cpu().numpy(), rtol=1e-5, atol=1e-5)
+        samples = maf.apply(params, cond[0], num_samples=10_000, key=0, method="sample")
+        assert samples.shape == (10_000, 3)
+        samples = maf.apply(params, cond[0].reshape((-1, n_cond)), num_samples=10_000, key=0, method="sample")
+        assert samples.shape == (10_000, 3)
+        assert torch.isfinite(samples).all()
+
+
+def test_forward_matches_oracle_at_trained_scale():
+    from jaxili_b200 import layout
+    from jaxili_b200.model import ConditionalMAF
+    maf = ConditionalMAF(4, 3, 3, [32, 16, 24], activation="tanh", use_reverse=True, seed=7)
+    rng = np.random.default_rng(1)
+    spec = onp.MafSpec(4, 3, 3, [32, 16, 24], activation="tanh", use_reverse=True, seed=7)
+    flat = spec.init_params(rng, 0.3, np.float32)
+    tree = layout.tree_from_flat(torch.tensor(flat, device="cuda:0"), maf.dims, 3)
+    x = rng.standard_normal((37, 4)).astype(np.float32)
+    y = rng.standard_normal((37, 3)).astype(np.float32)
+    u, ld = maf.apply({"params": tree}, x, y)
+    u_ref, ld_ref = onp.maf_forward(spec, flat.astype(np.float64), x.astype(np.float64), y.astype(np.float64))
+    assert rel_err(u.cpu().numpy(), u_ref) < 1e-5 and rel_err(ld.cpu().numpy(), ld_ref) < 1e-5
+    xr, ldr = maf.apply({"params": tree}, u_ref.astype(np.float32), y, method="backward")
+    x_ref, ldr_ref = onp.maf_inverse(spec, flat.astype(np.float64), u_ref, y.astype(np.float64))
+    assert rel_err(xr.cpu().numpy(), x_ref) < 2e-5 and rel_err(ldr.cpu().numpy(), ldr_ref) < 2e-5
+    # a tree of plain numpy leaves (e.g. loaded from a jaxili checkpoint) is accepted too
+    lp = maf.apply({"params": layout.tree_to_numpy(tree)}, x, y, method="log_prob")
+    assert rel_err(lp.cpu().numpy(), onp.maf_log_prob(spec, flat.astype(np.float64), x.astype(np.float64), y.astype(np.float64))) < 1e-5
+
+
+def test_network_w_standardization_like_reference():
+    """jaxili/tests/test_nn.py:182-237."""
+    from jaxili_b200 import nn
+    from jaxili_b200.model import ConditionalMAF, Identity, NDE_w_Standardization, ScalarAffine
+    n_in, n_cond = 2, 5
+    rng = np.random.default_rng(0)
+    theta = rng.standard_normal((10, n_in)).astype(np.float32)
+    x = rng.standard_normal((10, n_cond)).astype(np.float32)
+    shift = (rng.standard_normal(n_in) * 2).astype(np.float32)
+    scale = rng.standard_normal(n_in).astype(np.float32)
+    shifted_theta = theta * scale + shift
+    maf = ConditionalMAF(n_in=n_in, n_cond=n_cond, n_layers=3, layers=[50, 50], activation=nn.relu,
+                         use_reverse=True, seed=42)
+    net = NDE_w_Standardization(nde=maf, embedding_net=Identity(), transformation=ScalarAffine(scale=scale, shift=shift))
+    params = net.init(0, theta, x)
+    npt.assert_allclose(net.apply(params, shifted_theta, method="standardize").cpu().numpy(), theta, rtol=1e-5, atol=1e-5)
+    npt.assert_allclose(net.apply(params, theta, method="unstandardize").cpu().numpy(), shifted_theta, rtol=1e-5, atol=1e-5)
+    npt.assert_allclose(net.apply(params, x, method="embedding").cpu().numpy(), x, rtol=1e-5, atol=1e-5)
+    assert net.apply(params, theta, x, method="log_prob").shape == (10,)
+    assert net.apply(params, x[0], num_samples=10_000, key=0, method="sample").shape == (10_000, n_in)
+    # negative scale entries: log|scale| and the sign are handled as distrax does
+    spec = onp.MafSpec(n_in, n_cond, 3, [50, 50], seed=42)
+    flat = net.flat_params(params).cpu().numpy()
+    std = onp.Standardization(shift, scale, np.zeros(n_cond), np.ones(n_cond))
+    ref = onp.nde_log_prob(spec, flat.astype(np.float64), std, shifted_theta.astype(np.float64), x.astype(np.float64))
+    assert rel_err(net.apply(params, shifted_theta, x, method="log_prob").cpu().numpy(), ref) < 1e-5
+
+
+def test_trainer_steps_match_oracle(tmp_path):
+    """TrainerModule.train_step (host batches) == oracle loss / clip / schedule / Adam for 5 steps."""
+    from jaxili_b200 import nn
+    from jaxili_b200.loss import loss_nll_npe
+    from jaxili_b200.model import ConditionalMAF, Identity, NDE_w_Standardization, ScalarAffine, Sequential, Standardizer
+    from jaxili_b200.train import TrainerModule
+    theta, x = _sim(1024, seed=3)
+    sh, sc = theta.mean(0), theta.std(0)
+    me, sd = x.mean(0), x.std(0)
+    maf = ConditionalMAF(10, 10, 5, [50, 50], activation=nn.relu, use_reverse=True, seed=42)
+    hp = {"nde": maf, "embedding_net": Sequential([Standardizer(me, sd), Identity()]),
+          "transformation": ScalarAffine(shift=sh, scale=sc)}
+    tr = TrainerModule(NDE_w_Standardization, hp, {"lr": 5e-4, "gradient_clip": 5.0, "warmup": 0.1, "weight_decay": 0.0},
+                       loss_nll_npe, (np.zeros((1, 10), np.float32), np.zeros((1, 10), np.float32)),
+                       logger_params={"base_log_dir": str(tmp_path)}, enable_progress_bar=False)
+    tr.init_optimizer(num_epochs=2**31 - 1, num_steps_per_epoch=4)
+    spec = onp.MafSpec(10, 10, 5, [50, 50], seed=42)
+    std = onp.Standardization(sh, sc, me, sd)
+    ref = tr.state.params.flat.cpu().numpy().astype(np.float64)
+    st = onp.AdamState(ref.size, np.float64)
+    decay = float(int((2**31 - 1) // 2 * 4))
+    for i in range(5):
+        b = [theta[i * 200:(i + 1) * 200], x[i * 200:(i + 1) * 200]]
+        tr.state, m = tr.train_step(tr.state, b)
+        l_ref, g_ref = onp.nll_loss_and_grad(spec, ref, std, b[0].astype(np.float64), b[1].astype(np.float64))
+        assert rel_err(m["loss"].item(), l_ref) < 2e-5
+        ref, _, _ = onp.clip_adam_step(ref, g_ref, st, 5e-4, 0.1, decay)
+    assert np.max(np.abs(tr.state.params.flat.cpu().numpy() - ref)) < 5e-6
+    ev = tr.eval_step(tr.state, [theta[:300], x[:300]])
+    assert rel_err(ev["loss"].item(), onp.nll_loss(spec, ref, std, theta[:300].astype(np.float64), x[:300].astype(np.float64))) < 2e-5
+    # checkpoint round trip in the flax path layout
+    tr.save_model(step=1)
+    z = np.load(os.path.join(tr.log_dir, "checkpoint.npz"))
+    assert "params/nde/layer_list_0/ConditionalMADE_0/layers_0/Dense_0/kernel" in z.files
+    assert z["params/nde/layer_list_4/ConditionalMADE_0/layers_4/Dense_0/bias"].shape == (20,)
+    before = tr.state.params.flat.clone()
+    tr.state.params.flat.zero_()
+    tr.load_model()
+    assert torch.equal(tr.state.params.flat, before)
+
+
+def test_graph_step_equals_eager_steps(tmp_path):
+    from jaxili_b200 import nn
+    from jaxili_b200.loss import loss_nll_npe
+    from jaxili_b200.model import ConditionalMAF, Identity, NDE_w_Standardization, ScalarAffine, Sequential, Standardizer
+    from jaxili_b200.train import TrainerModule
+    theta, x = _sim(4 * 512, seed=5)
+
+    def mk():
+        maf = ConditionalMAF(10, 10, 5, [50, 50], activation=nn.relu, use_reverse=True, seed=42)
+        hp = {"nde": maf, "embedding_net": Sequential([Standardizer(x.mean(0), x.std(0)), Identity()]),
+              "transformation": ScalarAffine(shift=theta.mean(0), scale=theta.std(0))}
+        tr = TrainerModule(NDE_w_Standardization, hp, {"lr": 1e-3, "warmup": 0.1}, loss_nll_npe,
+                           (np.zeros((1, 10), np.float32), np.zeros((1, 10), np.float32)),
+                           logger_params={"base_log_dir": str(tmp_path)}, enable_progress_bar=False)
+        tr.init_optimizer(100, 4)
+        return tr
+    a, b = mk(), mk()
+    step = a.make_graph_step(torch.tensor(theta, device="cuda:0"), torch.tensor(x, device="cuda:0"), 512)
+    # make_graph_step ran the body twice already (warm-up + capture run nothing); count = device step
+    n0 = int(a.state.step.item())
+    for _ in range(6):
+        step()
+    n1 = int(a.state.step.item())
+    assert n1 - n0 == 6
+    for s in range(n1):
+        i = s % 4
+        b.state, _ = b.train_step(b.state, [theta[i * 512:(i + 1) * 512], x[i * 512:(i + 1) * 512]])
+    assert torch.allclose(a.state.params.flat, b.state.params.flat, rtol=0, atol=1e-6)
+
+
+def test_npe_end_to_end(tmp_path):
+    """jaxili/tests/test_npe.py:38-220 in one flow: split bookkeeping, loaders, standardisation,
+    training smoke test (metrics, files), density estimator and DirectPosterior surface."""
+    from jaxili_b200.inference import NPE, default_maf_hparams
+    from jaxili_b200.model import ConditionalMAF
+    from jaxili_b200.posterior import DirectPosterior
+    theta, x = _sim(10_000, seed=7)
+    inference = NPE(verbose=False)
+    assert inference._model_class == ConditionalMAF and inference._model_hparams is default_maf_hparams
+    inference = inference.append_simulations(theta, x, key=0)
+    assert (inference._dim_params, inference._dim_cond, inference._num_sims) == (10, 10, 10_000)
+    assert (len(inference._train_dataset), len(inference._val_dataset), len(inference._test_dataset)) == (7000, 2000, 1000)
+    inference._create_data_loader(batch_size=64)
+    assert next(iter(inference._train_loader))[0].shape[0] == 64
+    del inference._train_loader
+    model = inference._build_neural_network()
+    params = model.init(0, theta, x)
+    ttheta = inference._train_dataset.theta
+    std_theta = (ttheta - ttheta.mean(0)) / ttheta.std(0)
+    npt.assert_allclose(model.apply(params, ttheta, method="standardize").cpu().numpy(), std_theta, rtol=1e-5, atol=1e-5)
+    tx = inference._train_dataset.x
+    npt.assert_allclose(model.apply(params, tx, method="embedding").cpu().numpy(), (tx - tx.mean(0)) / tx.std(0), rtol=1e-5, atol=2e-5)
+    assert model.apply(params, ttheta, tx, method="log_prob").shape[0] == 7000
+    ckpt = str(tmp_path / "ck")
+    metrics, density_estimator = inference.train(training_batch_size=256, learning_rate=2e-3, num_epochs=12,
+                                                 checkpoint_path=ckpt, z_score_x=True)
+    assert metrics is not None and np.isfinite(metrics["val/loss"]) and np.isfinite(metrics["train/loss"])
+    assert "test/loss" in metrics
+    assert density_estimator.log_prob(theta[:10], x[:10]).shape == (10,)
+    assert density_estimator.sample(x[0], num_samples=10_000, key=0).shape == (10_000, 10)
+    base = os.path.join(ckpt, "NDE_w_Standardization/version_0")
+    assert os.path.exists(os.path.join(base, "metrics")) and os.path.exists(os.path.join(base, "hparams.json"))
+    assert json.load(open(os.path.join(base, "hparams.json")))["loss_fn"] == "loss_nll_npe"
+    posterior = inference.build_posterior()
+    assert isinstance(posterior, DirectPosterior)
+    with pytest.raises(ValueError):
+        posterior.sample(10, key=0)
+    posterior.set_default_x(x[0])
+    s = posterior.sample(5000, key=1)
+    assert s.shape == (5000, 10) and torch.isfinite(s).all()
+    # training moved the loss well below the untrained flow's NLL on the same validation data
+    fresh = model.apply(params, inference._val_dataset.theta, inference._val_dataset.x, method="log_prob")
+    assert metrics["val/loss"] < float(-fresh.mean()) - 0.5
+    lp = posterior.unnormalized_log_prob(s[:100])
+    assert lp.shape == (100,)
+    with pytest.raises(ValueError):
+        posterior.unnormalized_log_prob(s[:100], x=x[:7])
+
+
+def test_nle_end_to_end(tmp_path):
+    from jaxili_b200.inference import NLE
+    rng = np.random.default_rng(2)
+    theta = rng.uniform(-3, 3, size=(4000, 5)).astype(np.float32)
+    x = (np.repeat(theta[:, :2], 4, axis=1) + 0.3 * rng.standard_normal((4000, 8))).astype(np.float32)
+    inf = NLE(verbose=False).append_simulations(theta, x, key=1)
+    assert (inf._dim_params, inf._dim_cond) == (8, 5)
+    metrics, de = inf.train(training_batch_size=200, num_epochs=2, checkpoint_path=str(tmp_path / "nle"))
+    assert np.isfinite(metrics["val/loss"])
+    like = inf.build_posterior(x=x[0])
+    ll = like.log_likelihood(x[0], theta[:50])
+    assert ll.shape == (50,) and torch.isfinite(ll).all()
+    # training lowers the NLL: true theta explains x[0] better than a far-away theta
+    far = theta[:1].copy() + 2.5
+    assert like.log_likelihood(x[0], theta[:1]).item() > like.log_likelihood(x[0], far).item()
+    with pytest.raises(NotImplementedError):
+        like.sample(10)
+
+
+def test_errors_like_reference():
+    from jaxili_b200.inference import NPE
+    from jaxili_b200.model import ConditionalMAF
+    inf = NPE(verbose=False)
+    with pytest.raises(ValueError):
+        inf.train()
+    with pytest.raises(ValueError):
+        inf.build_posterior()
+    with pytest.raises(AssertionError):
+        inf.append_simulations(np.zeros((5, 2)), np.zeros((5, 2), np.float32))   # float64 theta
+    with pytest.raises(AssertionError):
+        inf.append_simulations(np.zeros((5, 2), np.float32), np.zeros((6, 2), np.float32))
+    with pytest.raises(ValueError):
+        ConditionalMAF(2, 2, 2, [8], activation="not_an_activation")
+    with pytest.raises(ValueError):
+        ConditionalMAF(1, 2, 2, [8], activation="relu", seed=1).engine()   # n_in=1: randint(0,0) in jaxili
