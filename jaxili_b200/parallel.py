@@ -1,0 +1,56 @@
+"""Data-parallel plumbing: one process per GPU, ``torch.distributed`` for the exchange.
+
+Training shards the global batch by contiguous row blocks; every rank computes
+``sum_local d(-log p)/dp * (1/B_global)`` with the fused kernel, then ONE all-reduce (sum) of the flat
+gradient buffer (P floats + the loss in the padding slot) makes the gradient global; the global-norm
+clip and the Adam update run redundantly on every rank on the reduced gradient, so replicas stay
+bit-identical.  log_prob evaluation and sampling shard by rows / observations with no collective.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def world_info():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_rows(n_rows, rank=None, world=None):
+    """Contiguous row block [start, stop) of rank ``rank``; blocks differ by at most one row."""
+    if rank is None or world is None:
+        rank, world = world_info()
+    base, rem = divmod(n_rows, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def inv_global_batch(local_rows):
+    """1 / B_global for equal-sized local batches (the trainer's drop_last batches)."""
+    _, world = world_info()
+    return 1.0 / (local_rows * world)
+
+
+def allreduce_grad_(gbuf):
+    """Sum the flat gradient(+loss) buffer over ranks, in place; no-op for a single process."""
+    _, world = world_info()
+    if world > 1:
+        dist.all_reduce(gbuf, op=dist.ReduceOp.SUM)
+    return gbuf
+
+
+def dp_step(compute_local, apply_update, gbuf):
+    """One data-parallel optimisation step: local fused fwd+bwd -> all-reduce -> replicated update."""
+    compute_local(gbuf)
+    allreduce_grad_(gbuf)
+    apply_update(gbuf)
+    return gbuf
+
+
+def philox_row_offset(rank_start_row):
+    """Sampling shards by rows: Philox subsequence = global row index, so samples do not depend on
+    the number of GPUs."""
+    return int(rank_start_row)

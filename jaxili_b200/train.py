@@ -31,7 +31,7 @@ from typing import Any, Callable, Dict, Iterator, Optional
 import numpy as np
 import torch
 
-from . import layout
+from . import layout, parallel
 from .loss import jaxili_loss_dict, loss_nll_nle, loss_nll_npe
 from .model import NDE_w_Standardization, ConditionalMAF, key_to_seed
 from .nn import jax_nn_dict
@@ -277,8 +277,6 @@ class TrainerModule:
 
     def create_functions(self):
         """jaxili/train.py:317-342."""
-        dist = torch.distributed
-
         def train_step(state: TrainState, batch: Any):
             if state.tx is None:
                 raise ValueError("optimizer not initialised: call init_optimizer / train_model first")
@@ -289,13 +287,13 @@ class TrainerModule:
             flat = state.params.flat
             P = flat.numel()
             grad, loss = self._gbuf[:P], self._gbuf[-4:-3]
-            world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-            eng.loss_grad(flat, x, y, loss, grad, inv_global_b=1.0 / (x.shape[0] * world),
-                          packed_current=self._packed)
-            if world > 1:
-                dist.all_reduce(self._gbuf)   # one NCCL all-reduce: flat gradient + loss
-            eng.clip_adam(flat, grad, state.opt_state["m"], state.opt_state["v"], state.step, state.tx,
-                          norm_current=world == 1)
+            _, world = parallel.world_info()
+            parallel.dp_step(
+                lambda g: eng.loss_grad(flat, x, y, loss, grad, inv_global_b=parallel.inv_global_batch(x.shape[0]),
+                                        packed_current=self._packed),
+                lambda g: eng.clip_adam(flat, grad, state.opt_state["m"], state.opt_state["v"], state.step,
+                                        state.tx, norm_current=world == 1),
+                self._gbuf)                   # one NCCL all-reduce: flat gradient + loss
             self._packed = True
             return state, {"loss": loss[0].clone()}
 

@@ -1,0 +1,249 @@
+"""CPU tests of the host-side logic and of the C-ABI boundary (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from jaxili_b200 import _lib, layout, masks, parallel
+from oracle import maf_numpy as onp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from jaxili_b200 import build
+    path = build.build()
+    assert os.path.isfile(path)
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "mafb200.h")).read()
+    declared = set(re.findall(r"\b(mafb200_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    raw = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in include/mafb200.h but not exported"
+    assert declared == set(_lib.SYMBOLS), "ctypes table and header disagree"
+    assert lib.mafb200_version() >= 100
+    assert lib.mafb200_last_error() is not None
+
+
+def test_product_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from jaxili_b200.engine import MafEngine
+    with pytest.raises(_lib.MafB200Error):
+        MafEngine(2, 2, 2, [8])
+    from jaxili_b200.model import ConditionalMAF
+    with pytest.raises(_lib.MafB200Error):
+        ConditionalMAF(2, 2, 2, [8], activation="relu", seed=1).init(0)
+    # the C entry point reports the missing device itself (no CPU fallback behind the ABI either)
+    lib = _lib.load()
+    desc = _lib.MafDesc()
+    desc.n_in, desc.n_cond, desc.n_layers, desc.n_hidden = 2, 2, 1, 1
+    desc.hidden[0] = 4
+    deg = np.zeros(4, np.int32)
+    h = ctypes.c_void_p()
+    rc = lib.mafb200_create(ctypes.byref(desc), deg.ctypes.data_as(ctypes.c_void_p), None, None, None, None, 0,
+                            ctypes.byref(h))
+    assert rc != 0 and b"no CPU fallback" in lib.mafb200_last_error()
+
+
+def test_product_does_not_import_the_oracle():
+    """oracle/ is test infrastructure: nothing under jaxili_b200/ may reference it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "jaxili_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
+
+
+def test_degrees_and_masks_match_oracle():
+    for n_in, n_cond, L, hid in [(10, 10, 5, [50, 50]), (2, 2, 5, [50, 50]), (8, 5, 5, [50, 50]), (3, 5, 4, [128, 128]),
+                                 (6, 0, 2, [16, 8, 12])]:
+        np.random.seed(999)                   # the builder must not disturb the caller's global RNG state
+        before = np.random.get_state()[1].copy()
+        deg = masks.maf_degrees(n_in, hid, L, 42)
+        assert (np.random.get_state()[1] == before).all()
+        spec = onp.MafSpec(n_in, n_cond, L, hid, seed=42)
+        assert masks.maf_layer_seeds(42, L) == spec.seeds
+        for k in range(L):
+            for a, b in zip(masks.masks_from_degrees(n_in, n_cond, hid, deg[k]), spec.masks[k]):
+                assert (a == b).all()
+    with pytest.raises(ValueError):
+        masks.made_hidden_degrees(1, [4], 0)
+
+
+def test_layout_round_trip_and_flax_paths():
+    dims, L = [20, 50, 50, 20], 5
+    P = layout.n_params(dims, L)
+    assert P == 23100
+    flat = torch.arange(P, dtype=torch.float32)
+    tree = layout.tree_from_flat(flat, dims, L, wrap_nde=True)
+    paths = layout.flatten_paths(tree)
+    assert "nde/layer_list_0/ConditionalMADE_0/layers_0/Dense_0/kernel" in paths
+    assert "nde/layer_list_4/ConditionalMADE_0/layers_4/Dense_0/bias" in paths
+    assert len(paths) == 5 * 3 * 2
+    assert paths["nde/layer_list_0/ConditionalMADE_0/layers_0/Dense_0/kernel"].shape == (20, 50)
+    assert paths["nde/layer_list_0/ConditionalMADE_0/layers_2/Dense_0/kernel"][0, 1] == 20 * 50 + 50 + 1
+    # views: writing a leaf writes the flat buffer
+    paths["nde/layer_list_1/ConditionalMADE_0/layers_0/Dense_0/bias"][3] = -7
+    assert flat[4620 + 1000 + 3] == -7
+    assert layout.flat_from_tree(tree, dims, L) is flat
+    rebuilt = layout.flat_from_tree(layout.unflatten_paths(layout.flatten_paths(layout.tree_to_numpy(tree))), dims, L)
+    assert torch.equal(rebuilt, flat)
+    # the oracle uses the same flat order
+    spec = onp.MafSpec(10, 10, 5, [50, 50])
+    lay = spec.unflatten(flat.numpy())
+    assert (lay[1][0][1] == tree["nde"]["layer_list_1"]["ConditionalMADE_0"]["layers_0"]["Dense_0"]["bias"].numpy()).all()
+    with pytest.raises(ValueError):
+        bad = layout.tree_to_numpy(tree)
+        bad["nde"]["layer_list_0"]["ConditionalMADE_0"]["layers_0"]["Dense_0"]["kernel"] = np.zeros((3, 3))
+        layout.flat_from_tree(bad, dims, L)
+
+
+def test_early_stopping_known_answers():
+    """Notebook known answers: best epoch 45 -> stop at 66 with patience 20."""
+    from jaxili_b200.train import EarlyStopping
+    for best in (45, 75, 249, 189):
+        es = EarlyStopping(min_delta=1e-3, patience=20)
+        stopped = None
+        for epoch in range(1, 1000):
+            metric = 1.0 - 0.01 * epoch if epoch <= best else 1.0 - 0.01 * best + 1e-4
+            es = es.update(metric)
+            if es.should_stop:
+                stopped = epoch
+                break
+        assert stopped == best + 21
+    es = EarlyStopping(min_delta=1e-3, patience=2).update(1.0)
+    assert es.has_improved and not es.update(0.9995).has_improved   # improvement below min_delta does not count
+
+
+def test_split_sizes_and_loaders():
+    """Split sizes follow the reference's int() arithmetic: 35000/9999/5001 for N = 50000
+    (notebooks/npe_validation.ipynb:1875-1879); loaders: shuffle+drop_last for train only."""
+    from jaxili_b200.inference.npe import NDEDataset, split_indices
+    from jaxili_b200.utils import create_data_loader, numpy_collate, validate_theta_x
+    tr, va, te = split_indices(50_000, [0.7, 0.2, 0.1], key=0)
+    assert (len(tr), len(va), len(te)) == (35_000, 9_999, 5_001)
+    assert len(set(tr) | set(va) | set(te)) == 50_000
+    tr2, va2, te2 = split_indices(1000, [0.7, 0.3], key=1)
+    assert te2 is None and len(tr2) + len(va2) == 1000
+    with pytest.raises(ValueError):
+        split_indices(10, [1.0], key=0)
+    with pytest.raises(AssertionError):
+        split_indices(10, [0.5, 0.2, 0.1], key=0)
+    theta = np.arange(300, dtype=np.float32).reshape(100, 3)
+    x = -theta[:, :2].copy()
+    ds = NDEDataset(theta, x)
+    train, val = create_data_loader(ds, ds, train=[True, False], batch_size=32)
+    assert len(train) == 3 and len(val) == 4
+    batches = list(train)
+    assert all(b[0].shape == (32, 3) and b[1].shape == (32, 2) for b in batches)
+    assert all((b[1] == -b[0][:, :2]).all() for b in batches)            # rows stay paired
+    first_epoch = np.concatenate([b[0][:, 0] for b in batches])
+    second_epoch = np.concatenate([b[0][:, 0] for b in train])
+    assert not np.array_equal(first_epoch, second_epoch)                 # reshuffled every epoch
+    vb = list(val)
+    assert vb[-1][0].shape[0] == 4 and (np.concatenate([b[0] for b in vb]) == theta).all()
+    assert numpy_collate([(np.ones(2), np.zeros(1)), (np.ones(2), np.zeros(1))])[0].shape == (2, 2)
+    with pytest.raises(AssertionError):
+        validate_theta_x(theta.astype(np.float64), x)
+    with pytest.raises(AssertionError):
+        validate_theta_x(theta, x[:5])
+    with pytest.raises(AssertionError):
+        validate_theta_x(list(theta), x)
+
+
+def test_keys_activations_and_sharding():
+    from jaxili_b200 import nn
+    from jaxili_b200.model import key_to_seed
+    assert key_to_seed(7) == 7 and key_to_seed(None) == 0
+    assert key_to_seed(np.array([0, 42], dtype=np.uint32)) == 42
+    assert key_to_seed(np.array([1, 2], dtype=np.uint32)) == (1 << 32) ^ 2
+    assert nn.activation_name(nn.relu) == "relu" and nn.activation_name("swish") == "silu"
+
+    def custom(x):
+        return x
+    with pytest.raises(ValueError):
+        nn.activation_name(custom)
+    assert set(nn.jax_nn_dict) >= {"relu", "silu", "tanh", "gelu", "elu", "sigmoid", "softplus", "leaky_relu"}
+    # row sharding covers every row exactly once
+    for n, w in [(10, 3), (16384, 8), (5, 8)]:
+        blocks = [parallel.shard_rows(n, r, w) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        assert max(b[1] - b[0] for b in blocks) - min(b[1] - b[0] for b in blocks) <= 1
+
+
+def test_bench_helpers_flops():
+    """SURVEY 8(d) algorithmic FLOP table."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.train_flops_per_sample(bench.WORKLOADS["c1"][0]) == 87_000
+    assert bench.train_flops_per_sample(bench.WORKLOADS["c2"][0]) == 135_000
+    assert bench.train_flops_per_sample(bench.WORKLOADS["c3"][0]) == 118_500
+    assert bench.sample_flops_per_sample(bench.WORKLOADS["c4"][0]) == 450_000
+    th, x = bench.synth_data("c3", bench.WORKLOADS["c3"][0], 100, 0)
+    assert th.shape == (100, 5) and x.shape == (100, 8) and x.dtype == np.float32
+
+
+_DP_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from jaxili_b200 import parallel
+from oracle import maf_numpy as onp
+from tests.util import CONFIGS, make_case
+rank, world = int(sys.argv[2]), int(sys.argv[3])
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[4]}", rank=rank, world_size=world)
+spec, flat, std, x, y = make_case(CONFIGS["c3"], 48, seed=9)
+P = spec.n_params
+params = flat.astype(np.float64)
+st = onp.AdamState(P, np.float64)
+lo, hi = parallel.shard_rows(48, rank, world)
+assert hi - lo == 24
+gbuf = torch.zeros(P + 1, dtype=torch.float64)
+for step in range(3):
+    def compute_local(g):
+        l, gr = onp.nll_loss_and_grad(spec, params, std, x[lo:hi].astype(np.float64), y[lo:hi].astype(np.float64),
+                                      inv_b=parallel.inv_global_batch(hi - lo))
+        g[:P] = torch.from_numpy(gr); g[P] = l
+    def apply_update(g):
+        global params
+        params, _, _ = onp.clip_adam_step(params, g[:P].numpy(), st, 1e-2, 0.1, 100, clip=0.5)
+    parallel.dp_step(compute_local, apply_update, gbuf)
+np.save(sys.argv[5] + f"/rank{rank}.npy", np.concatenate([params, [gbuf[P].item()]]))
+dist.destroy_process_group()
+'''
+
+
+def test_data_parallel_world_size_2_gloo(tmp_path):
+    """N>1 host path on CPU: two gloo ranks with the oracle standing in for the kernels; replicas end
+    bit-identical and equal to the single-process run on the global batch."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_DP_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(r), "2", str(port), str(tmp_path)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    for p in procs:
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out.decode()[-2000:]
+    a, b = np.load(tmp_path / "rank0.npy"), np.load(tmp_path / "rank1.npy")
+    assert np.array_equal(a, b)
+    from tests.util import CONFIGS, make_case
+    spec, flat, std, x, y = make_case(CONFIGS["c3"], 48, seed=9)
+    params = flat.astype(np.float64)
+    st = onp.AdamState(spec.n_params, np.float64)
+    for _ in range(3):
+        loss, g = onp.nll_loss_and_grad(spec, params, std, x.astype(np.float64), y.astype(np.float64))
+        params, _, _ = onp.clip_adam_step(params, g, st, 1e-2, 0.1, 100, clip=0.5)
+    assert np.max(np.abs(a[:-1] - params)) < 1e-12
+    assert abs(a[-1] - loss) < 1e-12 * abs(loss)
