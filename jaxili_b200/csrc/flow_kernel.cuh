@@ -33,19 +33,32 @@ struct FlowArgs {
   int Rt;                     // rows per tile in this launch (multiple of 4, <= Plan::R)
   int rb_shift;               // log2 of the power of two >= Rt/4 (row blocks per warp slot group)
   int n_tiles;
+  // per-linear work-list geometry, precomputed on the host (no integer division in the kernel)
+  struct Phase {
+    int fB;                   // forward: warp blocks
+    int xC, xB;               // input gradient: column blocks, warp blocks
+    int nKB, nNB;             // weight gradient: tile grid ((K+1)/4 x N/4, rounded up)
+    int nb_shift, nbg, nKG;   // column blocks per half-warp = 1<<nb_shift (<= 8), groups, row groups
+    int bB;                   // weight gradient: warp blocks = nKG * nbg
+  } ph[MAFB_MAX_LIN];
   long long* trace;           // debug: clock64 stamps of CTA 0 at phase boundaries (nullable)
 };
 
-// Every micro-GEMM uses 4x4 register tiles.  The reduction dimension is split over lane groups
-// of a warp (4 ways for the forward / input-gradient products, 2 ways for the weight-gradient
-// products) and recombined with warp-shuffle reduce-scatters: more parallel work units and
-// shorter dependent chains than one tile per thread, which is what the small per-SM row count
-// (28 rows at B=4096) needs.  Work units are mapped to (warp, lane) with shifts and masks only.
+// Every micro-GEMM uses 4x4 register tiles.  The reduction dimension is split over the two
+// half-warps and recombined with a warp-shuffle reduce-scatter: twice the parallel work units and
+// half the dependent chain of one tile per thread, which the small per-SM row count (28 rows at
+// B=4096) needs.  The lane -> tile maps are chosen for shared-memory MULTICAST: lanes of one load
+// instruction share operand rows (8 row blocks x 2 column blocks for h.W and G.W^T; 2 x 8 tile
+// groups for [A;1]^T G), which keeps the kernel at >= 5 FFMA per LSU wavefront -- the 128 B/clk
+// shared-memory port, not the FMA pipe, is what a naive mapping saturates first.  Work units are
+// mapped to (warp, lane) with shifts and masks only; the work-list geometry comes from the host.
 constexpr int TS = 4;           // tile side
-constexpr int KS = 4;           // lane groups splitting the reduction of outer-form products
+constexpr int KS = 2;           // lane groups splitting the reduction of outer-form products
 constexpr float kHalfLog2Pi = 0.9189385332046727f;
 
-template <bool BWD, bool RELU, int NT>
+// NLIN > 0 fixes the number of masked linears per MADE at compile time (loops over them unroll and
+// the per-linear descriptors become constant-bank operands); NLIN == 0 reads it from the plan.
+template <bool BWD, bool RELU, int NT, int NLIN>
 __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1)
 maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -56,15 +69,16 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = NT / 32;
-  const int D = P.D, C = P.C, L = P.L, RP = P.RP, n_lin = P.n_lin;
+  const int D = P.D, C = P.C, L = P.L, RP = P.RP;
+  const int n_lin = NLIN > 0 ? NLIN : P.n_lin;
   const int Rt = A.Rt;
   const int nRB = Rt / TS;
-  // outer-form products: a warp holds 8 tile slots x 4 reduction lanes; slot -> (row block, col block)
-  const int kq = lane >> 3;
-  const int slot8 = lane & 7;
-  const int o_rb = slot8 & ((1 << A.rb_shift) - 1);
-  const int o_cbl = slot8 >> A.rb_shift;          // column block within the warp's group
-  const int o_cpw = 8 >> A.rb_shift;              // column blocks per warp
+  // outer-form products: a warp holds 16 tile slots x 2 reduction lanes; slot -> (row block, col block)
+  const int kq = lane >> 4;
+  const int slot16 = lane & 15;
+  const int o_rb = slot16 & ((1 << A.rb_shift) - 1);
+  const int o_cbl = slot16 >> A.rb_shift;         // column block within the warp's group
+  const int o_cpw = 16 >> A.rb_shift;             // column blocks per warp
   const bool o_rok = o_rb < nRB;
   const int o_r0 = (o_rok ? o_rb : 0) * TS;
   const long long row_base =
@@ -177,7 +191,9 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
   //      (no log-det accumulation, no hand-off of v to the next layer).
   auto layer_forward = [&](int k, const float* wf, float* slot, bool replay) {
     const float* in = sm + P.o_xin + k * P.xin_stride;
-    for (int i = 0; i < n_lin; ++i) {
+#pragma unroll
+    for (int i = 0; i < (NLIN > 0 ? NLIN : MAFB_MAX_LIN); ++i) {
+      if (NLIN == 0 && i >= n_lin) break;
       const LinDesc& ln = P.lin[i];
       const float* W = wf + ln.w_off;
       const float* bias = wf + ln.b_off;
@@ -186,30 +202,33 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
       const bool last = i == n_lin - 1;
       float* hout = last ? obuf : slot + P.h_off[i + 1];
       float* dout = slot + P.d_off[last ? 1 : i + 1];
-      for (int cb0 = warp * o_cpw; cb0 < nCB; cb0 += NW * o_cpw) {
-        const int cb = cb0 + o_cbl;
+      for (int blk = warp; blk < A.ph[i].fB; blk += NW) {
+        const int cb = blk * o_cpw + o_cbl;
         const bool ok = o_rok && cb < nCB;
         const int c0 = (cb < nCB ? cb : nCB - 1) * TS;
-        float acc[TS][TS], res[TS];
+        float acc[TS][TS], res[2][TS];
         stamp(30);
         mm_outer_acc<TS, TS>(acc, in, Q, RP, W, CP, o_r0, c0, kq, KS);
         stamp(31);
-        reduce_scatter4(acc, kq, res);
+        reduce_scatter2(acc, kq, res);
         stamp(32);
-        if (ok) {   // lane kq finishes tile column kq
-          const int c = c0 + kq;
-          const float bj = bias[c];
-          if (!last) {
-            float hv[TS], dv[TS];
+        if (ok) {   // half-warp kq finishes tile columns 2kq, 2kq+1
 #pragma unroll
-            for (int q = 0; q < TS; ++q) act_eval<RELU>(P.act, res[q] + bj, hv[q], dv[q]);
-            stv(hout + c * RP + o_r0, hv);
-            if (!RELU && BWD) stv(dout + c * RP + o_r0, dv);
-          } else {
-            float ov[TS];
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = c0 + 2 * kq + cc;
+            const float bj = bias[c];
+            if (!last) {
+              float hv[TS], dv[TS];
 #pragma unroll
-            for (int q = 0; q < TS; ++q) ov[q] = res[q] + bj;
-            stv(hout + c * RP + o_r0, ov);
+              for (int q = 0; q < TS; ++q) act_eval<RELU>(P.act, res[cc][q] + bj, hv[q], dv[q]);
+              stv(hout + c * RP + o_r0, hv);
+              if (!RELU && BWD) stv(dout + c * RP + o_r0, dv);
+            } else {
+              float ov[TS];
+#pragma unroll
+              for (int q = 0; q < TS; ++q) ov[q] = res[cc][q] + bj;
+              stv(hout + c * RP + o_r0, ov);
+            }
           }
         }
       }
@@ -341,57 +360,59 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
         __syncthreads();
         stamp(5);
 
-        for (int i = n_lin - 1; i >= 0; --i) {
+#pragma unroll
+        for (int ii = 0; ii < (NLIN > 0 ? NLIN : MAFB_MAX_LIN); ++ii) {
+          const int i = n_lin - 1 - ii;
+          if (NLIN == 0 && i < 0) break;
           const LinDesc& ln = P.lin[i];
           const float* G = (i == n_lin - 1) ? obuf : sm + P.o_g[i & 1];
           const float* Ain = (i == 0) ? xin : slot + P.h_off[i];
           const float* Wt = wb + ln.wt_off;
           // two warp-granular work lists share the phase:
-          //   X: input gradient g_in = G (M*W)^T; a warp holds 8 tiles, 4 lanes split the sum over n
-          //   B: weight + bias gradient [A;1]^T G; a warp holds 16 tiles (one row of 16 column
-          //      blocks), its two half-warps split the batch rows
-          const int nXC = ((i == 0) ? P.DP : ln.KP) / TS;
-          const int bX = (nXC + o_cpw - 1) / o_cpw;
+          //   X: input gradient g_in = G (M*W)^T; a warp holds 16 tiles, its half-warps split the sum over n
+          //   B: weight + bias gradient [A;1]^T G; a warp holds (16 >> nb_shift) x (1 << nb_shift) tiles,
+          //      its half-warps split the batch rows
+          const FlowArgs::Phase& ph = A.ph[i];
           const int N = ln.N, K = ln.K, KP = ln.KP;
-          const int nKB = (K + 1 + TS - 1) / TS, nNB = (N + TS - 1) / TS;
-          const int nbg = (nNB + 15) >> 4;             // groups of 16 column blocks
-          // narrow outputs: several row blocks kb share a warp (16 >> nb_shift of them)
-          const int nb_shift = nNB > 8 ? 4 : (nNB > 4 ? 3 : (nNB > 2 ? 2 : (nNB > 1 ? 1 : 0)));
-          const int kpw = 16 >> nb_shift;
-          const int bB = nbg == 1 ? (nKB + kpw - 1) / kpw : nKB * nbg;
-          for (int blk = warp; blk < bX + bB; blk += NW) {
+          const int bX = ph.xB, nXC = ph.xC;
+          for (int blk = warp; blk < bX + ph.bB; blk += NW) {
+            stamp(blk < bX ? 40 : 42);
             if (blk < bX) {
               const int cb = blk * o_cpw + o_cbl;
               const bool ok = o_rok && cb < nXC;
               const int c0 = (cb < nXC ? cb : nXC - 1) * TS;
-              float acc[TS][TS], res[TS];
+              float acc[TS][TS], res[2][TS];
               mm_outer_acc<TS, TS>(acc, G, N, RP, Wt, KP, o_r0, c0, kq, KS);
-              reduce_scatter4(acc, kq, res);
+              reduce_scatter2(acc, kq, res);
               if (ok) {
-                const int c = c0 + kq;
-                float dv[TS], gv[TS];
-                if (i > 0) {   // through the activation: g_a = g_h * act'(a)
-                  ldv(dv, slot + (RELU ? P.h_off[i] : P.d_off[i]) + c * RP + o_r0);
 #pragma unroll
-                  for (int q = 0; q < TS; ++q)
-                    gv[q] = RELU ? (dv[q] > 0.f ? res[q] : 0.f) : res[q] * dv[q];
-                  stv(sm + P.o_g[(i - 1) & 1] + c * RP + o_r0, gv);
-                } else {       // gradient w.r.t. this layer's input x: MADE path + direct path
-                  ldv(dv, gx + c * RP + o_r0);
+                for (int cc = 0; cc < 2; ++cc) {
+                  const int c = c0 + 2 * kq + cc;
+                  float dv[TS], gv[TS];
+                  if (i > 0) {   // through the activation: g_a = g_h * act'(a)
+                    ldv(dv, slot + (RELU ? P.h_off[i] : P.d_off[i]) + c * RP + o_r0);
 #pragma unroll
-                  for (int q = 0; q < TS; ++q) gv[q] = res[q] + dv[q];
-                  stv(gu + c * RP + o_r0, gv);
+                    for (int q = 0; q < TS; ++q)
+                      gv[q] = RELU ? (dv[q] > 0.f ? res[cc][q] : 0.f) : res[cc][q] * dv[q];
+                    stv(sm + P.o_g[(i - 1) & 1] + c * RP + o_r0, gv);
+                  } else {       // gradient w.r.t. this layer's input x: MADE path + direct path
+                    ldv(dv, gx + c * RP + o_r0);
+#pragma unroll
+                    for (int q = 0; q < TS; ++q) gv[q] = res[cc][q] + dv[q];
+                    stv(gu + c * RP + o_r0, gv);
+                  }
                 }
               }
             } else {
-              const int b = blk - bX;
+              int b = blk - bX, g = 0;
+              while (b >= ph.nKG) { b -= ph.nKG; ++g; }        // g < nbg <= a few
               const int l16 = lane & 15;
-              int kb, nb;
-              if (nbg == 1) { kb = b * kpw + (l16 >> nb_shift); nb = l16 & ((1 << nb_shift) - 1); }
-              else { kb = b / nbg; nb = (b - kb * nbg) * 16 + l16; }
-              mm_inner_rs2(Ain, K, KP, G, N, Rt, RP, kb, nKB, nb < nNB ? nb : nNB - 1, nNB, lane >> 4,
-                           nb < nNB && kb < nKB, pg + ln.pw_off, accum);
+              const int kb = b * (16 >> ph.nb_shift) + (l16 >> ph.nb_shift);
+              const int nb = (g << ph.nb_shift) + (l16 & ((1 << ph.nb_shift) - 1));
+              mm_inner_rs2(Ain, K, KP, G, N, Rt, RP, kb, ph.nKB, nb < ph.nNB ? nb : ph.nNB - 1, ph.nNB, lane >> 4,
+                           nb < ph.nNB && kb < ph.nKB, pg + ln.pw_off, accum);
             }
+            stamp(blk < bX ? 41 : 43);
           }
           __syncthreads();
           stamp(20 + i);

@@ -262,6 +262,20 @@ bool make_sample_plan(const MafDesc& d, const int* dims, SamplePlan& S) {
 
 }  // namespace
 
+template <bool BWD>
+static void launch_flow(const Plan& P, const FlowArgs& A, int grid, cudaStream_t st) {
+  const bool relu = P.act == MAFB200_ACT_RELU;
+#define LAUNCH(NT_, R_, L_) maf_flow_kernel<BWD, R_, NT_, L_><<<grid, NT_, P.smem_bytes, st>>>(P, A)
+#define PICK_L(NT_, R_) do { if (P.n_lin == 3) LAUNCH(NT_, R_, 3); else LAUNCH(NT_, R_, 0); } while (0)
+  if (P.threads == kFlowThreads2) {
+    if (relu) PICK_L(kFlowThreads2, true); else PICK_L(kFlowThreads2, false);
+  } else {
+    if (relu) PICK_L(kFlowThreads, true); else PICK_L(kFlowThreads, false);
+  }
+#undef PICK_L
+#undef LAUNCH
+}
+
 // ====================================================================== C ABI
 extern "C" {
 
@@ -401,17 +415,17 @@ int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shi
   }
 
   // opt in to the large dynamic shared memory carve-out for every kernel we may launch
-  const int sb = P.smem_bytes;
-  CUH(cudaFuncSetAttribute(maf_flow_kernel<true, true, kFlowThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-  CUH(cudaFuncSetAttribute(maf_flow_kernel<true, false, kFlowThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-  CUH(cudaFuncSetAttribute(maf_flow_kernel<false, true, kFlowThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-  CUH(cudaFuncSetAttribute(maf_flow_kernel<false, false, kFlowThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-  if (h->plan2.P) {
-    const int sb2 = h->plan2.smem_bytes;
-    CUH(cudaFuncSetAttribute(maf_flow_kernel<true, true, kFlowThreads2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb2));
-    CUH(cudaFuncSetAttribute(maf_flow_kernel<true, false, kFlowThreads2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb2));
-    CUH(cudaFuncSetAttribute(maf_flow_kernel<false, true, kFlowThreads2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb2));
-    CUH(cudaFuncSetAttribute(maf_flow_kernel<false, false, kFlowThreads2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb2));
+  {
+    const int sb = P.smem_bytes, sb2 = h->plan2.P ? h->plan2.smem_bytes : 0;
+#define SET_FLOW(B_, R_, L_)                                                                              \
+  CUH(cudaFuncSetAttribute(maf_flow_kernel<B_, R_, kFlowThreads, L_>,                                     \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, sb));                             \
+  if (sb2)                                                                                                \
+    CUH(cudaFuncSetAttribute(maf_flow_kernel<B_, R_, kFlowThreads2, L_>,                                  \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, sb2));
+    SET_FLOW(true, true, 3) SET_FLOW(true, false, 3) SET_FLOW(false, true, 3) SET_FLOW(false, false, 3)
+    SET_FLOW(true, true, 0) SET_FLOW(true, false, 0) SET_FLOW(false, true, 0) SET_FLOW(false, false, 0)
+#undef SET_FLOW
   }
   if (have_sampler) {
     CUH(cudaFuncSetAttribute(maf_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->splan.smem_bytes));
@@ -511,9 +525,9 @@ int mafb200_pack(mafb200_handle h, const float* params, void* stream) {
 static int launch_geometry(mafb200_handle h, int64_t B, const Plan*& plan, int& Rt, int& n_tiles, int& grid) {
   int occ = 1;
   if (h->plan2.P) {
-    // two CTAs per SM pay off while a single CTA per SM would hold at most a few tiles
-    occ = (B <= (int64_t)h->n_sm * 64) ? 2 : 1;
-    if (h->occ_mode == 1 || h->occ_mode == 2) occ = h->occ_mode;
+    // measured on B200 (tests/occ_bench.py): one 512-thread CTA per SM beats two 256-thread CTAs on
+    // c1-c3 at every batch size tried; the second plan stays selectable for experiments
+    if (h->occ_mode == 2) occ = 2;
   }
   plan = occ == 2 ? &h->plan2 : &h->plan;
   const int R = plan->R;
@@ -543,11 +557,29 @@ static int flow_timing_begin(mafb200_handle h, cudaStream_t st) {
   return 0;
 }
 
-static int rb_shift_for(int Rt) {
-  const int nRB = Rt / 4;
+// work-list geometry of one launch (see FlowArgs::Phase)
+static void fill_phases(const Plan& P, FlowArgs& A) {
+  const int nRB = A.Rt / 4;
   int s = 0;
-  while ((1 << s) < nRB) ++s;
-  return s;   // nRB <= 8 -> s <= 3
+  while ((1 << s) < nRB) ++s;          // nRB <= 8 -> s <= 3
+  A.rb_shift = s;
+  const int cpw = 16 >> s;             // column blocks per warp in the outer-form products
+  for (int i = 0; i < P.n_lin; ++i) {
+    const LinDesc& ln = P.lin[i];
+    FlowArgs::Phase& ph = A.ph[i];
+    ph.fB = (ln.NP / 4 + cpw - 1) / cpw;
+    ph.xC = (i == 0 ? P.DP : ln.KP) / 4;
+    ph.xB = (ph.xC + cpw - 1) / cpw;
+    ph.nKB = (ln.K + 1 + 3) / 4;
+    ph.nNB = (ln.N + 3) / 4;
+    int nbs = 0;
+    while ((1 << nbs) < ph.nNB && nbs < 3) ++nbs;   // at most 8 column blocks per half-warp
+    ph.nb_shift = nbs;
+    ph.nbg = (ph.nNB + (1 << nbs) - 1) >> nbs;
+    const int kpw = 16 >> nbs;
+    ph.nKG = (ph.nKB + kpw - 1) / kpw;
+    ph.bB = ph.nKG * ph.nbg;
+  }
 }
 
 int mafb200_forward(mafb200_handle h, const float* params, const float* x, const float* y, int64_t B,
@@ -574,17 +606,10 @@ int mafb200_forward(mafb200_handle h, const float* params, const float* x, const
   int grid;
   const Plan* pp;
   if (launch_geometry(h, B, pp, A.Rt, A.n_tiles, grid)) return 1;
-  A.rb_shift = rb_shift_for(A.Rt);
+  fill_phases(*pp, A);
   const Plan& P = *pp;
-  const bool relu = P.act == MAFB200_ACT_RELU;
   if (h->timing && flow_timing_begin(h, st)) return 1;
-  if (P.threads == kFlowThreads2) {
-    if (relu) maf_flow_kernel<false, true, kFlowThreads2><<<grid, kFlowThreads2, P.smem_bytes, st>>>(P, A);
-    else maf_flow_kernel<false, false, kFlowThreads2><<<grid, kFlowThreads2, P.smem_bytes, st>>>(P, A);
-  } else {
-    if (relu) maf_flow_kernel<false, true, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
-    else maf_flow_kernel<false, false, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
-  }
+  launch_flow<false>(P, A, grid, st);
   CU(cudaGetLastError());
   if (h->timing) CU(cudaEventRecord(h->ev1, st));
   return 0;
@@ -620,17 +645,10 @@ int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, con
   int grid;
   const Plan* pp;
   if (launch_geometry(h, B, pp, A.Rt, A.n_tiles, grid)) return 1;
-  A.rb_shift = rb_shift_for(A.Rt);
+  fill_phases(*pp, A);
   const Plan& P = *pp;
-  const bool relu = P.act == MAFB200_ACT_RELU;
   if (h->timing && flow_timing_begin(h, st)) return 1;
-  if (P.threads == kFlowThreads2) {
-    if (relu) maf_flow_kernel<true, true, kFlowThreads2><<<grid, kFlowThreads2, P.smem_bytes, st>>>(P, A);
-    else maf_flow_kernel<true, false, kFlowThreads2><<<grid, kFlowThreads2, P.smem_bytes, st>>>(P, A);
-  } else {
-    if (relu) maf_flow_kernel<true, true, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
-    else maf_flow_kernel<true, false, kFlowThreads><<<grid, kFlowThreads, P.smem_bytes, st>>>(P, A);
-  }
+  launch_flow<true>(P, A, grid, st);
   CU(cudaGetLastError());
   if (h->timing) CU(cudaEventRecord(h->ev1, st));
   reduce_kernel<<<h->n_norm, RED_IDX * RED_PARTS, 0, st>>>(h->partial, grid, P.P, h->mask, out_grad,
