@@ -13,6 +13,7 @@
 #include "flow_kernel.cuh"
 #include "opt_kernels.cuh"
 #include "sample_kernel.cuh"
+#include "wide_kernels.cuh"
 
 using namespace mafb;
 
@@ -63,6 +64,20 @@ struct mafb200_handle_s {
   float logdet_const = 0.f;
   int n_norm = 0;
   long long* trace = nullptr;   // debug: device buffer of 1001 int64 (set by mafb200_debug_trace)
+  // wide (layer-by-layer) path: used when the MADE does not fit shared memory
+  bool wide = false;
+  float* wm = nullptr;          // mask-folded copy of the parameters (flat layout)
+  long long wcap = 0;           // rows the scratch below is sized for
+  float* w_a0 = nullptr;        // [L][cap][K0]   per-layer MADE input [x_k | y']
+  float* w_h = nullptr;         // [L][sum H][cap] hidden activations, level-major inside a layer
+  float* w_d = nullptr;         // same shape: act'(a) (non-ReLU only)
+  float* w_s = nullptr;         // [L][cap][D]
+  float* w_v = nullptr;         // [L][cap][D]
+  float* w_o = nullptr;         // [cap][2D]
+  float* w_u = nullptr;         // [cap][D]  base-space point, then grad wrt layer output
+  float* w_gx = nullptr;        // [cap][D]
+  float* w_ld = nullptr;        // [cap]
+  float* w_g[2] = {nullptr, nullptr};   // [cap][max H] hidden-gradient ping-pong
   // optional CUDA-event bracket around the flow kernel alone (roofline measurement in bench.py)
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -207,6 +222,34 @@ bool make_plan(const MafDesc& d, const int* dims, Plan& P, int occ) {
   return false;
 }
 
+// model description only (no shared-memory layout): what the wide path needs of Plan
+void make_plan_dims_only(const MafDesc& d, const int* dims, Plan& P) {
+  std::memset(&P, 0, sizeof(P));
+  P.D = d.n_in;
+  P.C = d.n_cond;
+  P.K0 = d.n_in + d.n_cond;
+  P.L = d.n_layers;
+  P.n_lin = d.n_hidden + 1;
+  P.act = d.activation;
+  P.reverse = d.use_reverse ? 1 : 0;
+  P.DP = r4(P.D);
+  P.need_d = d.activation != MAFB200_ACT_RELU;
+  int po = 0;
+  for (int i = 0; i < P.n_lin; ++i) {
+    LinDesc& ln = P.lin[i];
+    ln.K = dims[i];
+    ln.N = dims[i + 1];
+    ln.KP = ln.K;
+    ln.NP = ln.N;
+    ln.pw_off = po;
+    po += ln.K * ln.N;
+    ln.pb_off = po;
+    po += ln.N;
+  }
+  P.ppl = po;
+  P.P = po * P.L;
+}
+
 // ------------------------------------------------------------------ sampler planner + sorted positions
 bool make_sample_plan(const MafDesc& d, const int* dims, SamplePlan& S) {
   std::memset(&S, 0, sizeof(S));
@@ -276,6 +319,202 @@ static void launch_flow(const Plan& P, const FlowArgs& A, int grid, cudaStream_t
 #undef LAUNCH
 }
 
+
+// ====================================================================== wide path orchestration
+namespace {
+
+constexpr long long kWideChunk = 65536;   // rows per pass through the layer chain
+
+int wide_ensure_scratch(mafb200_handle h, long long rows) {
+  const long long cap = std::min<long long>(kWideChunk, (rows + 127) / 128 * 128);
+  if (cap <= h->wcap) return 0;
+  const Plan& P = h->plan;
+  int hsum = 0, hmax = 4;
+  for (int i = 1; i < P.n_lin; ++i) { hsum += P.lin[i].K; hmax = std::max(hmax, P.lin[i].K); }
+  float** bufs[] = {&h->w_a0, &h->w_h, &h->w_d, &h->w_s, &h->w_v, &h->w_o, &h->w_u, &h->w_gx, &h->w_ld,
+                    &h->w_g[0], &h->w_g[1]};
+  for (float** b : bufs) { cudaFree(*b); *b = nullptr; }
+  h->wcap = 0;
+  const size_t c = (size_t)cap;
+  CU(cudaMalloc(&h->w_a0, (size_t)P.L * c * P.K0 * 4));
+  CU(cudaMalloc(&h->w_h, (size_t)P.L * c * hsum * 4));
+  if (P.need_d) CU(cudaMalloc(&h->w_d, (size_t)P.L * c * hsum * 4));
+  CU(cudaMalloc(&h->w_s, (size_t)P.L * c * P.D * 4));
+  CU(cudaMalloc(&h->w_v, (size_t)P.L * c * P.D * 4));
+  CU(cudaMalloc(&h->w_o, c * 2 * P.D * 4));
+  CU(cudaMalloc(&h->w_u, c * P.D * 4));
+  CU(cudaMalloc(&h->w_gx, c * P.D * 4));
+  CU(cudaMalloc(&h->w_ld, c * 4));
+  CU(cudaMalloc(&h->w_g[0], c * hmax * 4));
+  CU(cudaMalloc(&h->w_g[1], c * hmax * 4));
+  h->wcap = cap;
+  return 0;
+}
+
+template <bool A_KFAST, bool B_KFAST, int EPI>
+int wide_launch_gemm(const GemmArgs& g, bool relu, int splits, cudaStream_t st) {
+  const dim3 block(256);
+#define WG(BN_)                                                                                          \
+  do {                                                                                                   \
+    const dim3 grid((g.N + BN_ - 1) / BN_, (g.M + 127) / 128, splits);                                   \
+    if (relu) wide_gemm_kernel<BN_, A_KFAST, B_KFAST, EPI, true><<<grid, block, 0, st>>>(g);             \
+    else wide_gemm_kernel<BN_, A_KFAST, B_KFAST, EPI, false><<<grid, block, 0, st>>>(g);                 \
+  } while (0)
+  if (g.N > 64) WG(128);
+  else if (g.N > 32) WG(64);
+  else WG(32);
+#undef WG
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// one chunk of rows through the whole flow; bwd: also the reverse pass accumulating into grad / loss
+int wide_chunk(mafb200_handle h, const float* x, const float* y, long long rows, float inv_b, bool bwd,
+               float* out_logp, float* out_u, float* out_logdet, float* loss, float* grad, cudaStream_t st) {
+  const Plan& P = h->plan;
+  const bool relu = P.act == MAFB200_ACT_RELU;
+  const int D = P.D, K0 = P.K0, L = P.L, n_lin = P.n_lin;
+  const size_t cap = (size_t)h->wcap;
+  int hsum = 0;
+  for (int i = 1; i < n_lin; ++i) hsum += P.lin[i].K;
+  WideCommon w{D, P.C, K0, P.reverse, rows, inv_b, h->logdet_const};
+  const bool stash = bwd;
+  auto a0 = [&](int k) { return h->w_a0 + (size_t)(stash ? k : (k & 1)) * cap * K0; };
+  auto hbuf = [&](float* base, int k, int lvl) {   // hidden level lvl (1..n_hidden) of layer k
+    size_t off = (size_t)(stash ? k : 0) * cap * hsum;
+    for (int i = 1; i < lvl; ++i) off += cap * P.lin[i].K;
+    return base + off;
+  };
+  const long long a0_stride = (long long)cap * K0;
+  {
+    const long long n = rows * K0;
+    wide_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, x, y, h->stdc, h->w_a0, a0_stride,
+                                                                  stash ? L : 2, h->w_ld);
+    CU(cudaGetLastError());
+  }
+  // ---------------- forward
+  for (int k = 0; k < L; ++k) {
+    const float* wl = h->wm + (size_t)k * P.ppl;
+    const float* in = a0(k);
+    int ld_in = K0;
+    for (int i = 0; i < n_lin; ++i) {
+      const LinDesc& ln = P.lin[i];
+      GemmArgs g{};
+      g.A = in; g.lda = ld_in;
+      g.B = wl + ln.pw_off; g.ldb = ln.N;
+      g.M = (int)rows; g.N = ln.N; g.K = ln.K;
+      g.bias = wl + ln.pb_off;
+      g.act = P.act;
+      if (i < n_lin - 1) {
+        g.C = hbuf(h->w_h, k, i + 1); g.ldc = ln.N;
+        if (P.need_d && bwd) { g.aux_out = hbuf(h->w_d, k, i + 1); g.ldaux_out = ln.N; }
+        if (wide_launch_gemm<true, false, EPI_BIAS_ACT>(g, relu, 1, st)) return 1;
+        in = g.C; ld_in = ln.N;
+      } else {
+        g.C = h->w_o; g.ldc = ln.N;
+        if (wide_launch_gemm<true, false, EPI_BIAS>(g, relu, 1, st)) return 1;
+      }
+    }
+    float* xnext = (k + 1 < L) ? a0(k + 1) : h->w_u;
+    const int xld = (k + 1 < L) ? K0 : D;
+    wide_affine_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(
+        w, h->w_o, a0(k), bwd ? h->w_s + (size_t)k * cap * D : nullptr, bwd ? h->w_v + (size_t)k * cap * D : nullptr,
+        xnext, xld, h->w_ld);
+    CU(cudaGetLastError());
+  }
+  if (out_u) CU(cudaMemcpyAsync(out_u, h->w_u, (size_t)rows * D * 4, cudaMemcpyDeviceToDevice, st));
+  if (out_logdet) CU(cudaMemcpyAsync(out_logdet, h->w_ld, (size_t)rows * 4, cudaMemcpyDeviceToDevice, st));
+  wide_final_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w, h->w_u, h->w_ld, out_logp, bwd ? loss : nullptr,
+                                                                bwd ? h->w_u : nullptr);
+  CU(cudaGetLastError());
+  if (!bwd) return 0;
+  // ---------------- reverse pass
+  const int splits = (int)std::max<long long>(1, std::min<long long>(64, rows / 1024));
+  const int k_chunk = (int)(((rows + splits - 1) / splits + 7) / 8 * 8);
+  for (int k = L - 1; k >= 0; --k) {
+    const float* wl = h->wm + (size_t)k * P.ppl;
+    float* gl = grad + (size_t)k * P.ppl;
+    const unsigned char* ml = h->mask + (size_t)k * P.ppl;
+    {
+      const long long n = rows * D;
+      wide_bwd_elem_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+          w, h->w_u, h->w_s + (size_t)k * cap * D, h->w_v + (size_t)k * cap * D, h->w_o, h->w_gx);
+      CU(cudaGetLastError());
+    }
+    const float* G = h->w_o;
+    for (int i = n_lin - 1; i >= 0; --i) {
+      const LinDesc& ln = P.lin[i];
+      const float* Ain = (i == 0) ? a0(k) : hbuf(h->w_h, k, i);
+      {  // weight gradient: dW = M * (A^T G), rows split over blockIdx.z
+        GemmArgs g{};
+        g.A = Ain; g.lda = ln.K;
+        g.B = G; g.ldb = ln.N;
+        g.C = gl + ln.pw_off; g.ldc = ln.N;
+        g.M = ln.K; g.N = ln.N; g.K = (int)rows;
+        g.mask = ml + ln.pw_off;
+        g.k_chunk = k_chunk;
+        if (wide_launch_gemm<false, false, EPI_ATOMIC_MASK>(g, relu, (int)((rows + k_chunk - 1) / k_chunk), st)) return 1;
+        const int rpb = 512;
+        wide_colsum_kernel<<<dim3((ln.N + 127) / 128, (unsigned)((rows + rpb - 1) / rpb)), 128, 0, st>>>(
+            G, rows, ln.N, rpb, gl + ln.pb_off);
+        CU(cudaGetLastError());
+      }
+      {  // input gradient
+        GemmArgs g{};
+        g.A = G; g.lda = ln.N;
+        g.B = wl + ln.pw_off; g.ldb = ln.N;
+        g.M = (int)rows; g.K = ln.N;
+        g.act = P.act;
+        if (i > 0) {
+          g.N = ln.K;
+          g.C = h->w_g[i & 1]; g.ldc = ln.K;
+          g.aux = relu ? hbuf(h->w_h, k, i) : hbuf(h->w_d, k, i); g.ldaux = ln.K;
+          if (wide_launch_gemm<true, true, EPI_MUL_DERIV>(g, relu, 1, st)) return 1;
+          G = g.C;
+        } else {
+          g.N = D;                       // only the x part of the input carries gradient further
+          g.C = h->w_u; g.ldc = D;
+          g.aux = h->w_gx; g.ldaux = D;
+          if (wide_launch_gemm<true, true, EPI_ADD>(g, relu, 1, st)) return 1;
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+int wide_forward(mafb200_handle h, const float* params, const float* x, const float* y, int64_t B,
+                 float* out_logp, float* out_u, float* out_logdet, int32_t flags, cudaStream_t st) {
+  if (!(flags & MAFB200_PACKED_CURRENT) && mafb200_pack(h, params, st)) return 1;
+  if (wide_ensure_scratch(h, B)) return 1;
+  const Plan& P = h->plan;
+  for (int64_t r0 = 0; r0 < B; r0 += h->wcap) {
+    const long long rows = std::min<long long>(h->wcap, B - r0);
+    if (wide_chunk(h, x + r0 * P.D, y + r0 * P.C, rows, 1.f, false, out_logp ? out_logp + r0 : nullptr,
+                   out_u ? out_u + r0 * P.D : nullptr, out_logdet ? out_logdet + r0 : nullptr, nullptr, nullptr, st))
+      return 1;
+  }
+  return 0;
+}
+
+int wide_loss_grad(mafb200_handle h, const float* params, const float* x, const float* y, int64_t B,
+                   float inv_global_B, float* out_loss, float* out_grad, int32_t flags, cudaStream_t st) {
+  if (!(flags & MAFB200_PACKED_CURRENT) && mafb200_pack(h, params, st)) return 1;
+  if (wide_ensure_scratch(h, B)) return 1;
+  const Plan& P = h->plan;
+  CU(cudaMemsetAsync(out_grad, 0, (size_t)P.P * 4, st));
+  CU(cudaMemsetAsync(out_loss, 0, 4, st));
+  for (int64_t r0 = 0; r0 < B; r0 += h->wcap) {
+    const long long rows = std::min<long long>(h->wcap, B - r0);
+    if (wide_chunk(h, x + r0 * P.D, y + r0 * P.C, rows, inv_global_B, true, nullptr, nullptr, nullptr, out_loss,
+                   out_grad, st))
+      return 1;
+  }
+  return 0;
+}
+
+}  // namespace
+
 // ====================================================================== C ABI
 extern "C" {
 
@@ -331,13 +570,20 @@ int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shi
   h->dims[0] = d.n_in + d.n_cond;
   for (int i = 0; i < d.n_hidden; ++i) h->dims[i + 1] = d.hidden[i];
   h->dims[d.n_hidden + 1] = 2 * d.n_in;
-  if (!make_plan(d, h->dims, h->plan, 1)) {
-    delete h;
-    return fail("model too wide for the shared-memory-resident (narrow) path; wide tcgen05 path not built yet");
+  const char* force_wide = getenv("MAFB200_FORCE_WIDE");
+  if (!make_plan(d, h->dims, h->plan, 1) || (force_wide && atoi(force_wide))) {
+    // MADE too large for the shared-memory-resident kernel: layer-by-layer GEMM path
+    for (int i = 0; i <= d.n_hidden + 1; ++i)
+      if (h->dims[i] % 4) {
+        delete h;
+        return fail("wide path needs n_in, n_cond and all hidden sizes to be multiples of 4");
+      }
+    make_plan_dims_only(d, h->dims, h->plan);
+    h->wide = true;
   }
-  if (!make_plan(d, h->dims, h->plan2, 2) || !h->plan2.stash_all || h->plan2.R < 16) h->plan2.P = 0;
+  if (h->wide || !make_plan(d, h->dims, h->plan2, 2) || !h->plan2.stash_all || h->plan2.R < 16) h->plan2.P = 0;
   if (const char* e = getenv("MAFB200_OCC")) h->occ_mode = atoi(e);
-  const bool have_sampler = make_sample_plan(d, h->dims, h->splan);
+  const bool have_sampler = !h->wide && make_sample_plan(d, h->dims, h->splan);
   if (!have_sampler) h->splan.img_floats = 0;
   const Plan& P = h->plan;
   build_masks(d, degrees, h->mask_host, h->dims, P.n_lin, P.ppl);
@@ -352,10 +598,14 @@ int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shi
   } while (0)
   CUH(cudaMalloc(&h->mask, P.P));
   CUH(cudaMemcpy(h->mask, h->mask_host.data(), P.P, cudaMemcpyHostToDevice));
-  CUH(cudaMalloc(&h->wimg, (size_t)P.L * P.img_floats * 4));
-  CUH(cudaMemset(h->wimg, 0, (size_t)P.L * P.img_floats * 4));
+  if (h->wide) {
+    CUH(cudaMalloc(&h->wm, (size_t)P.P * 4));
+  } else {
+    CUH(cudaMalloc(&h->wimg, (size_t)P.L * P.img_floats * 4));
+    CUH(cudaMemset(h->wimg, 0, (size_t)P.L * P.img_floats * 4));
+  }
   CUH(cudaMalloc(&h->stdc, (3 * P.D + 2 * P.C) * 4));
-  CUH(cudaMalloc(&h->partial, (size_t)2 * h->n_sm * P.P * 4));
+  if (!h->wide) CUH(cudaMalloc(&h->partial, (size_t)2 * h->n_sm * P.P * 4));
   CUH(cudaMalloc(&h->partial_loss, 2 * h->n_sm * 4));
   h->n_norm = (P.P + RED_IDX - 1) / RED_IDX;
   CUH(cudaMalloc(&h->normpart, h->n_norm * 4));
@@ -415,7 +665,7 @@ int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shi
   }
 
   // opt in to the large dynamic shared memory carve-out for every kernel we may launch
-  {
+  if (!h->wide) {
     const int sb = P.smem_bytes, sb2 = h->plan2.P ? h->plan2.smem_bytes : 0;
 #define SET_FLOW(B_, R_, L_)                                                                              \
   CUH(cudaFuncSetAttribute(maf_flow_kernel<B_, R_, kFlowThreads, L_>,                                     \
@@ -453,6 +703,10 @@ int mafb200_destroy(mafb200_handle h) {
   cudaFree(h->partial_loss);
   cudaFree(h->normpart);
   cudaFree(h->done_counter);
+  cudaFree(h->wm);
+  cudaFree(h->w_a0); cudaFree(h->w_h); cudaFree(h->w_d); cudaFree(h->w_s); cudaFree(h->w_v);
+  cudaFree(h->w_o); cudaFree(h->w_u); cudaFree(h->w_gx); cudaFree(h->w_ld);
+  cudaFree(h->w_g[0]); cudaFree(h->w_g[1]);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
@@ -505,7 +759,7 @@ int mafb200_get_mask(mafb200_handle h, uint8_t* mask_host) {
 int mafb200_query(mafb200_handle h, int32_t* smem_bytes, int32_t* tile_rows, int32_t* max_ctas,
                   int32_t* stash_all) {
   if (!h) return fail("null handle");
-  if (smem_bytes) *smem_bytes = h->plan.smem_bytes;
+  if (smem_bytes) *smem_bytes = h->wide ? 0 : h->plan.smem_bytes;
   if (tile_rows) *tile_rows = h->plan.R;
   if (max_ctas) *max_ctas = h->n_sm;
   if (stash_all) *stash_all = h->plan.stash_all;
@@ -515,7 +769,10 @@ int mafb200_query(mafb200_handle h, int32_t* smem_bytes, int32_t* tile_rows, int
 int mafb200_pack(mafb200_handle h, const float* params, void* stream) {
   if (!h || !params) return fail("null argument");
   const Plan& P = h->plan;
-  pack_kernel<<<(P.P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, params, h->mask, h->wimg);
+  if (h->wide)
+    wide_pack_kernel<<<(P.P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params, h->mask, h->wm, P.P);
+  else
+    pack_kernel<<<(P.P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, params, h->mask, h->wimg);
   CU(cudaGetLastError());
   return 0;
 }
@@ -588,6 +845,7 @@ int mafb200_forward(mafb200_handle h, const float* params, const float* x, const
   if (!out_logp && !out_u && !out_logdet) return fail("no output requested");
   if (B <= 0) return B == 0 ? 0 : fail("negative batch");
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->wide) return wide_forward(h, params, x, y, B, out_logp, out_u, out_logdet, flags, st);
   if (!(flags & MAFB200_PACKED_CURRENT) && mafb200_pack(h, params, stream)) return 1;
   FlowArgs A{};
   A.wimg = h->wimg;
@@ -628,6 +886,13 @@ int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, con
   if (B <= 0) return fail("loss_grad needs a non-empty batch");
   if (batch_index && n_batches <= 0) return fail("n_batches must be positive");
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->wide) {
+    if (batch_index) return fail("device-side batch selection is not available on the wide path");
+    if (wide_loss_grad(h, params, x, y, B, inv_global_B, out_loss, out_grad, flags, st)) return 1;
+    sqnorm_kernel<<<h->n_norm, RED_IDX, 0, st>>>(out_grad, h->plan.P, h->normpart);
+    CU(cudaGetLastError());
+    return 0;
+  }
   if (!(flags & MAFB200_PACKED_CURRENT) && mafb200_pack(h, params, stream)) return 1;
   FlowArgs A{};
   A.wimg = h->wimg;
@@ -672,7 +937,8 @@ int mafb200_clip_adam(mafb200_handle h, float* params, const float* grad, float*
   OptArgs O{opt->lr, opt->warmup, opt->decay_steps, opt->init_factor, opt->end_factor, opt->b1, opt->b2,
             opt->eps, opt->clip, opt->weight_decay, opt->kind};
   clip_adam_kernel<<<h->n_norm, RED_IDX, 0, st>>>(P, O, params, grad, m, v, step, h->normpart, h->n_norm,
-                                                  h->mask, h->wimg, h->done_counter, nullptr);
+                                                  h->mask, h->wide ? h->wm : h->wimg, h->wide ? 1 : 0,
+                                                  h->done_counter, nullptr);
   CU(cudaGetLastError());
   return 0;
 }

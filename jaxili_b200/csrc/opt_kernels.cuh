@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(RED_IDX)
 clip_adam_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs O,
                  float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ m,
                  float* __restrict__ v, int* __restrict__ step, const float* __restrict__ normpart,
-                 int n_norm, const unsigned char* __restrict__ mask, float* __restrict__ wimg,
+                 int n_norm, const unsigned char* __restrict__ mask, float* __restrict__ wimg, int flat_image,
                  unsigned int* __restrict__ done_counter, float* __restrict__ gnorm_out) {
   __shared__ float wsum[RED_IDX / 32];
   __shared__ float s_norm;
@@ -185,7 +185,8 @@ clip_adam_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
     }
     p = p - lr_t * upd;
     params[idx] = p;
-    write_image(P, wimg, idx, mask[idx] ? p : 0.f);
+    if (flat_image) wimg[idx] = mask[idx] ? p : 0.f;      // wide path: masked copy, same layout
+    else write_image(P, wimg, idx, mask[idx] ? p : 0.f);
   }
   // the last block to finish bumps the optax count (all blocks have read step[0] by then)
   __syncthreads();

@@ -1,0 +1,314 @@
+// wide_kernels.cuh -- layer-by-layer ConditionalMAF path for models whose MADE does not fit shared
+// memory (e.g. BASELINE config 5: n_in=32, n_cond=128, hidden [512,512], 10 layers).
+//
+// Activations live in HBM (row-major [rows][features]); every masked linear is a tiled GEMM with a
+// fused epilogue (bias + activation, activation derivative, gradient masking).  The three product
+// shapes of the MADE are one kernel template:
+//   NN  C[m][n] = sum_k A[m][k]  W[k][n]      forward            h = act(a W' + b)
+//   NT  C[m][k] = sum_n G[m][n]  W[k][n]      input gradient     g_in = (G W'^T) * act'
+//   TN  C[k][n] = sum_m A[m][k]  G[m][n]      weight gradient    dW = M * (A^T G), split over rows
+// W' is the mask-folded copy of the parameters (same flat layout), refreshed by the optimizer.
+// This file is the FP32-FFMA core (exact parity with the oracle); the tcgen05 TF32 core replaces the
+// mainloop for the large shapes (wide_tc.cuh).
+#pragma once
+#include "common.cuh"
+
+namespace mafb {
+
+enum { EPI_BIAS_ACT = 0, EPI_BIAS = 1, EPI_MUL_DERIV = 2, EPI_ADD = 3, EPI_ATOMIC_MASK = 4 };
+
+struct GemmArgs {
+  const float* A; int lda;      // first operand
+  const float* B; int ldb;      // second operand
+  float* C; int ldc;            // output
+  int M, N, K;                  // C is M x N, reduction length K
+  const float* bias;            // EPI_BIAS*: [N]
+  const float* aux; int ldaux;  // EPI_MUL_DERIV: h or act' [M x N]; EPI_ADD: addend [M x N]
+  float* aux_out; int ldaux_out;  // EPI_BIAS_ACT with derivative output (non-ReLU): act'(a)
+  const unsigned char* mask;    // EPI_ATOMIC_MASK: [M x N] (ld = N)
+  int act;
+  int k_chunk;                  // TN: reduction rows per CTA (split-K over blockIdx.z)
+};
+
+// 128 x BN x 8 tiles, 256 threads, 8 x (BN/16) outputs per thread, register-prefetched double buffer.
+// TA: A tile is read with the reduction index as the fast (contiguous) global dimension (NN, NT);
+//     otherwise the output-row index is contiguous (TN).
+// TB: likewise for B (NT: reduction index contiguous; NN, TN: output-column index contiguous).
+template <int BN, bool A_KFAST, bool B_KFAST, int EPI, bool RELU>
+__global__ void __launch_bounds__(256) wide_gemm_kernel(const __grid_constant__ GemmArgs g) {
+  constexpr int BM = 128, BK = 8, TN = BN / 16;
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  int k_begin = 0, k_end = g.K;
+  if (EPI == EPI_ATOMIC_MASK) {
+    k_begin = blockIdx.z * g.k_chunk;
+    k_end = min(g.K, k_begin + g.k_chunk);
+  }
+  const int tm = (tid / 16) * 8, tn = (tid % 16) * TN;
+
+  // global -> register staging: each thread moves one float4 of A (128x8 = 256 float4) and
+  // BN*8/4/256 float4 of B per k-step
+  float4 ra;
+  float4 rb[(BN * BK / 4 + 255) / 256];
+  auto load_tiles = [&](int k0) {
+    if (A_KFAST) {   // A[m][k..k+3]: thread -> (m = tid/2, kq = tid%2)
+      const int m = m0 + tid / 2, k = k0 + (tid % 2) * 4;
+      ra = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < g.M) {
+        const float* p = g.A + (size_t)m * g.lda + k;
+        if (k + 3 < k_end) ra = *reinterpret_cast<const float4*>(p);
+        else {
+          if (k < k_end) ra.x = p[0];
+          if (k + 1 < k_end) ra.y = p[1];
+          if (k + 2 < k_end) ra.z = p[2];
+        }
+      }
+    } else {         // A[k][m..m+3]: thread -> (k = tid/32, mq = tid%32)
+      const int k = k0 + tid / 32, m = m0 + (tid % 32) * 4;
+      ra = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < k_end) {
+        const float* p = g.A + (size_t)k * g.lda + m;
+        if (m + 3 < g.M) ra = *reinterpret_cast<const float4*>(p);
+        else {
+          if (m < g.M) ra.x = p[0];
+          if (m + 1 < g.M) ra.y = p[1];
+          if (m + 2 < g.M) ra.z = p[2];
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < (BN * BK / 4 + 255) / 256; ++it) {
+      const int idx = tid + it * 256;
+      rb[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < BN * BK / 4) {
+        if (B_KFAST) {   // B[n][k..k+3]
+          const int n = n0 + idx / 2, k = k0 + (idx % 2) * 4;
+          if (n < g.N) {
+            const float* p = g.B + (size_t)n * g.ldb + k;
+            if (k + 3 < k_end) rb[it] = *reinterpret_cast<const float4*>(p);
+            else {
+              if (k < k_end) rb[it].x = p[0];
+              if (k + 1 < k_end) rb[it].y = p[1];
+              if (k + 2 < k_end) rb[it].z = p[2];
+            }
+          }
+        } else {         // B[k][n..n+3]
+          const int k = k0 + idx / (BN / 4), n = n0 + (idx % (BN / 4)) * 4;
+          if (k < k_end) {
+            const float* p = g.B + (size_t)k * g.ldb + n;
+            if (n + 3 < g.N) rb[it] = *reinterpret_cast<const float4*>(p);
+            else {
+              if (n < g.N) rb[it].x = p[0];
+              if (n + 1 < g.N) rb[it].y = p[1];
+              if (n + 2 < g.N) rb[it].z = p[2];
+            }
+          }
+        }
+      }
+    }
+  };
+  auto store_tiles = [&](int buf) {
+    if (A_KFAST) {
+      const int m = tid / 2, k = (tid % 2) * 4;
+      As[buf][k][m] = ra.x; As[buf][k + 1][m] = ra.y; As[buf][k + 2][m] = ra.z; As[buf][k + 3][m] = ra.w;
+    } else {
+      const int k = tid / 32, m = (tid % 32) * 4;
+      *reinterpret_cast<float4*>(&As[buf][k][m]) = ra;
+    }
+#pragma unroll
+    for (int it = 0; it < (BN * BK / 4 + 255) / 256; ++it) {
+      const int idx = tid + it * 256;
+      if (idx < BN * BK / 4) {
+        if (B_KFAST) {
+          const int n = idx / 2, k = (idx % 2) * 4;
+          Bs[buf][k][n] = rb[it].x; Bs[buf][k + 1][n] = rb[it].y; Bs[buf][k + 2][n] = rb[it].z; Bs[buf][k + 3][n] = rb[it].w;
+        } else {
+          const int k = idx / (BN / 4), n = (idx % (BN / 4)) * 4;
+          *reinterpret_cast<float4*>(&Bs[buf][k][n]) = rb[it];
+        }
+      }
+    }
+  };
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int nk = (k_end - k_begin + BK - 1) / BK;
+  if (nk > 0) {
+    load_tiles(k_begin);
+    store_tiles(0);
+  }
+  __syncthreads();
+  for (int s = 0; s < nk; ++s) {
+    const int buf = s & 1;
+    if (s + 1 < nk) load_tiles(k_begin + (s + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float av[8], bv[TN];
+      ldv(*reinterpret_cast<float(*)[4]>(&av[0]), &As[buf][kk][tm]);
+      ldv(*reinterpret_cast<float(*)[4]>(&av[4]), &As[buf][kk][tm + 4]);
+      if (TN == 8) {
+        ldv(*reinterpret_cast<float(*)[4]>(&bv[0]), &Bs[buf][kk][tn]);
+        ldv(*reinterpret_cast<float(*)[4]>(&bv[TN - 4]), &Bs[buf][kk][tn + TN - 4]);
+      } else if (TN == 4) {
+        ldv(*reinterpret_cast<float(*)[4]>(&bv[0]), &Bs[buf][kk][tn]);
+      } else {
+        ldv(*reinterpret_cast<float(*)[2]>(&bv[0]), &Bs[buf][kk][tn]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (s + 1 < nk) store_tiles(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- fused epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + tm + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tn + j;
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      if (EPI == EPI_BIAS_ACT) {
+        float h, d;
+        act_eval<RELU>(g.act, v + g.bias[n], h, d);
+        g.C[(size_t)m * g.ldc + n] = h;
+        if (!RELU && g.aux_out) g.aux_out[(size_t)m * g.ldaux_out + n] = d;
+      } else if (EPI == EPI_BIAS) {
+        g.C[(size_t)m * g.ldc + n] = v + g.bias[n];
+      } else if (EPI == EPI_MUL_DERIV) {
+        const float a = g.aux[(size_t)m * g.ldaux + n];
+        g.C[(size_t)m * g.ldc + n] = RELU ? (a > 0.f ? v : 0.f) : v * a;
+      } else if (EPI == EPI_ADD) {
+        g.C[(size_t)m * g.ldc + n] = v + g.aux[(size_t)m * g.ldaux + n];
+      } else {   // EPI_ATOMIC_MASK: masked weight gradient, rows split over blockIdx.z
+        if (g.mask[(size_t)m * g.N + n]) atomicAdd(&g.C[(size_t)m * g.ldc + n], v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ elementwise pieces
+struct WideCommon {
+  int D, C, K0, reverse;
+  long long B;
+  float inv_b, logdet_const;
+};
+
+// standardise x, y into the first layer's input [x' | y'] and copy y' into every layer's input
+__global__ void wide_prep_kernel(WideCommon w, const float* __restrict__ x, const float* __restrict__ y,
+                                 const float* __restrict__ stdc, float* __restrict__ a0, long long a0_stride,
+                                 int L, float* __restrict__ ld) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= w.B * w.K0) return;
+  const long long r = idx / w.K0;
+  const int j = (int)(idx - r * w.K0);
+  if (j < w.D) {
+    a0[r * w.K0 + j] = (x[r * w.D + j] - stdc[j]) * stdc[w.D + j];
+    if (j == 0) ld[r] = 0.f;
+  } else {
+    const int c = j - w.D;
+    const float v = __fdiv_rn(y[r * w.C + c] - stdc[2 * w.D + c], stdc[2 * w.D + w.C + c]);
+    for (int l = 0; l < L; ++l) a0[l * a0_stride + r * w.K0 + j] = v;
+  }
+}
+
+// affine autoregressive transform of one layer (jaxili/model.py:739-742): o = [mu | logp]
+__global__ void wide_affine_kernel(WideCommon w, const float* __restrict__ o, const float* __restrict__ a0k,
+                                   float* __restrict__ s_out, float* __restrict__ v_out,
+                                   float* __restrict__ xnext, int xnext_ld, float* __restrict__ ld) {
+  const long long r = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  if (r >= w.B) return;
+  const int lane = threadIdx.x & 31;
+  float lsum = 0.f;
+  for (int j = lane; j < w.D; j += 32) {
+    const float mu = o[r * 2 * w.D + j], lp = o[r * 2 * w.D + w.D + j];
+    const float s = expf(0.5f * lp);
+    const float v = (a0k[r * w.K0 + j] - mu) * s;
+    if (s_out) { s_out[r * w.D + j] = s; v_out[r * w.D + j] = v; }
+    const int jj = w.reverse ? w.D - 1 - j : j;
+    xnext[r * xnext_ld + jj] = v;
+    lsum += 0.5f * lp;
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) ld[r] += lsum;
+}
+
+// log-probability per row, NLL accumulation, seed of the reverse pass (g_u = u / B)
+__global__ void wide_final_kernel(WideCommon w, const float* __restrict__ u, const float* __restrict__ ld,
+                                  float* __restrict__ out_logp, float* __restrict__ loss, float* __restrict__ gu) {
+  const long long r = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  float contrib = 0.f;
+  if (r < w.B) {
+    float acc = 0.f;
+    for (int j = lane; j < w.D; j += 32) {
+      const float uv = u[r * w.D + j];
+      acc += uv * uv;
+      if (gu) gu[r * w.D + j] = uv * w.inv_b;
+    }
+    acc = warp_sum(acc);
+    const float lp = -0.5f * acc - (float)w.D * 0.9189385332046727f + ld[r] + w.logdet_const;
+    if (lane == 0) {
+      if (out_logp) out_logp[r] = lp;
+      contrib = -lp * w.inv_b;
+    }
+  }
+  if (loss) {
+    __shared__ float red[8];
+    if (lane == 0) red[threadIdx.x / 32] = contrib;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < blockDim.x / 32; ++i) t += red[i];
+      atomicAdd(loss, t);
+    }
+  }
+}
+
+// gradient w.r.t. the MADE outputs of one layer and the direct path to x
+__global__ void wide_bwd_elem_kernel(WideCommon w, const float* __restrict__ gu, const float* __restrict__ s_in,
+                                     const float* __restrict__ v_in, float* __restrict__ go,
+                                     float* __restrict__ gxdir) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= w.B * w.D) return;
+  const long long r = idx / w.D;
+  const int j = (int)(idx - r * w.D);
+  const int jj = w.reverse ? w.D - 1 - j : j;
+  const float gv = gu[r * w.D + jj];
+  const float s = s_in[idx], v = v_in[idx];
+  go[r * 2 * w.D + j] = -gv * s;
+  go[r * 2 * w.D + w.D + j] = 0.5f * gv * v - 0.5f * w.inv_b;
+  gxdir[idx] = gv * s;
+}
+
+// bias gradient: column sums of G [M x N] accumulated into db[N]
+__global__ void wide_colsum_kernel(const float* __restrict__ G, long long M, int N, int rows_per_block,
+                                   float* __restrict__ db) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) s += G[r * N + n];
+  atomicAdd(&db[n], s);
+}
+
+// mask-folded copy of the parameters in the same flat layout (the wide path's "image")
+__global__ void wide_pack_kernel(const float* __restrict__ params, const unsigned char* __restrict__ mask,
+                                 float* __restrict__ wm, int P) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < P) wm[idx] = mask[idx] ? params[idx] : 0.f;
+}
+
+}  // namespace mafb
