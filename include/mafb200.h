@@ -124,6 +124,17 @@ int mafb200_debug_trace(mafb200_handle h, long long* trace_dev);
 int mafb200_flow_timing(mafb200_handle h, int32_t enable);
 int mafb200_flow_elapsed(mafb200_handle h, double* total_ms, int64_t* launches);
 
+/* Models whose MADE does not fit shared memory run layer by layer ("wide" path).  Its GEMM core is
+   tcgen05 TF32 (core = 1, default; FP32 accumulate, operands truncated to TF32: log_prob agrees
+   with FP32 to ~1e-3 absolute) or FP32 FFMA (core = 0, same 1e-5 tolerance as the
+   fused narrow kernel).  No effect on models that use the fused kernel. */
+int mafb200_set_wide_core(mafb200_handle h, int32_t core);
+
+/* test hook: one GEMM of the wide path (see mafb200.cu); not part of the reference-facing surface */
+int mafb200_debug_gemm(int32_t variant, int32_t core, const float* A, const float* B, float* C,
+                       int32_t M, int32_t N, int32_t K, const float* zeros_n, const float* zeros_mn,
+                       const uint8_t* mask, void* stream);
+
 int64_t mafb200_param_count(mafb200_handle h);
 /* writes the 0/1 mask in flat parameter order (biases 1) to a host buffer of param_count bytes */
 int mafb200_get_mask(mafb200_handle h, uint8_t* mask_host);

@@ -14,6 +14,7 @@
 #include "opt_kernels.cuh"
 #include "sample_kernel.cuh"
 #include "wide_kernels.cuh"
+#include "wide_tc.cuh"
 
 using namespace mafb;
 
@@ -66,6 +67,7 @@ struct mafb200_handle_s {
   long long* trace = nullptr;   // debug: device buffer of 1001 int64 (set by mafb200_debug_trace)
   // wide (layer-by-layer) path: used when the MADE does not fit shared memory
   bool wide = false;
+  int wide_core = 1;            // 1: tcgen05 TF32 GEMM core, 0: FP32 FFMA core (exact)
   float* wm = nullptr;          // mask-folded copy of the parameters (flat layout)
   long long wcap = 0;           // rows the scratch below is sized for
   float* w_a0 = nullptr;        // [L][cap][K0]   per-layer MADE input [x_k | y']
@@ -368,6 +370,80 @@ int wide_launch_gemm(const GemmArgs& g, bool relu, int splits, cudaStream_t st) 
   return 0;
 }
 
+
+// ---------------------------------------------------------------- tcgen05 core: tensor maps + launch
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// FP32 matrix [outer][inner] with row stride ld floats; box = box_inner x box_outer, 128-byte swizzle
+int make_tmap(CUtensorMap* m, const float* base, long long inner, long long outer, long long ld, int box_inner,
+              int box_outer, bool mn_major) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail("cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return 0;
+}
+
+// A_MN / B_MN: operand stored with the OUTPUT index contiguous ([reduction][output] row-major)
+template <bool A_MN, bool B_MN, int EPI>
+int wide_launch_tc(const GemmArgs& g, bool relu, int splits, cudaStream_t st) {
+  CUtensorMap ta, tb;
+  // K-major: inner = reduction (g.K), outer = output rows; MN-major: inner = output, outer = reduction
+  if (A_MN ? make_tmap(&ta, g.A, g.M, g.K, g.lda, 32, 32, true) : make_tmap(&ta, g.A, g.K, g.M, g.lda, 32, TC_BM, false))
+    return 1;
+#define WTC(BN_)                                                                                           \
+  do {                                                                                                     \
+    if (B_MN ? make_tmap(&tb, g.B, g.N, g.K, g.ldb, 32, 32, true) : make_tmap(&tb, g.B, g.K, g.N, g.ldb, 32, BN_, false)) \
+      return 1;                                                                                            \
+    const dim3 grid((g.N + BN_ - 1) / BN_, (g.M + TC_BM - 1) / TC_BM, splits);                             \
+    static bool attr_t = false, attr_f = false;                                                            \
+    if (relu) {                                                                                            \
+      auto kfn = wide_tc_gemm_kernel<BN_, A_MN, B_MN, EPI, true>;                                          \
+      if (!attr_t) { CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN_>::SMEM_BYTES)); attr_t = true; } \
+      kfn<<<grid, 192, TcCfg<BN_>::SMEM_BYTES, st>>>(ta, tb, g);                                           \
+    } else {                                                                                               \
+      auto kfn = wide_tc_gemm_kernel<BN_, A_MN, B_MN, EPI, false>;                                         \
+      if (!attr_f) { CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN_>::SMEM_BYTES)); attr_f = true; } \
+      kfn<<<grid, 192, TcCfg<BN_>::SMEM_BYTES, st>>>(ta, tb, g);                                           \
+    }                                                                                                      \
+  } while (0)
+  if (g.N > 64) WTC(128);
+  else if (g.N > 32) WTC(64);
+  else WTC(32);
+#undef WTC
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// dispatch: <A reduction-contiguous?, B reduction-contiguous?> of the FFMA core <-> <A_MN, B_MN> of the TC core
+template <bool A_KFAST, bool B_KFAST, int EPI>
+int wide_gemm(mafb200_handle h, const GemmArgs& g, bool relu, int splits, cudaStream_t st) {
+  if (h->wide_core == 1) return wide_launch_tc<!A_KFAST, !B_KFAST, EPI>(g, relu, splits, st);
+  return wide_launch_gemm<A_KFAST, B_KFAST, EPI>(g, relu, splits, st);
+}
+
 // one chunk of rows through the whole flow; bwd: also the reverse pass accumulating into grad / loss
 int wide_chunk(mafb200_handle h, const float* x, const float* y, long long rows, float inv_b, bool bwd,
                float* out_logp, float* out_u, float* out_logdet, float* loss, float* grad, cudaStream_t st) {
@@ -408,11 +484,11 @@ int wide_chunk(mafb200_handle h, const float* x, const float* y, long long rows,
       if (i < n_lin - 1) {
         g.C = hbuf(h->w_h, k, i + 1); g.ldc = ln.N;
         if (P.need_d && bwd) { g.aux_out = hbuf(h->w_d, k, i + 1); g.ldaux_out = ln.N; }
-        if (wide_launch_gemm<true, false, EPI_BIAS_ACT>(g, relu, 1, st)) return 1;
+        if (wide_gemm<true, false, EPI_BIAS_ACT>(h, g, relu, 1, st)) return 1;
         in = g.C; ld_in = ln.N;
       } else {
         g.C = h->w_o; g.ldc = ln.N;
-        if (wide_launch_gemm<true, false, EPI_BIAS>(g, relu, 1, st)) return 1;
+        if (wide_gemm<true, false, EPI_BIAS>(h, g, relu, 1, st)) return 1;
       }
     }
     float* xnext = (k + 1 < L) ? a0(k + 1) : h->w_u;
@@ -430,7 +506,7 @@ int wide_chunk(mafb200_handle h, const float* x, const float* y, long long rows,
   if (!bwd) return 0;
   // ---------------- reverse pass
   const int splits = (int)std::max<long long>(1, std::min<long long>(64, rows / 1024));
-  const int k_chunk = (int)(((rows + splits - 1) / splits + 7) / 8 * 8);
+  const int k_chunk = (int)(((rows + splits - 1) / splits + 31) / 32 * 32);
   for (int k = L - 1; k >= 0; --k) {
     const float* wl = h->wm + (size_t)k * P.ppl;
     float* gl = grad + (size_t)k * P.ppl;
@@ -453,7 +529,7 @@ int wide_chunk(mafb200_handle h, const float* x, const float* y, long long rows,
         g.M = ln.K; g.N = ln.N; g.K = (int)rows;
         g.mask = ml + ln.pw_off;
         g.k_chunk = k_chunk;
-        if (wide_launch_gemm<false, false, EPI_ATOMIC_MASK>(g, relu, (int)((rows + k_chunk - 1) / k_chunk), st)) return 1;
+        if (wide_gemm<false, false, EPI_ATOMIC_MASK>(h, g, relu, (int)((rows + k_chunk - 1) / k_chunk), st)) return 1;
         const int rpb = 512;
         wide_colsum_kernel<<<dim3((ln.N + 127) / 128, (unsigned)((rows + rpb - 1) / rpb)), 128, 0, st>>>(
             G, rows, ln.N, rpb, gl + ln.pb_off);
@@ -469,13 +545,13 @@ int wide_chunk(mafb200_handle h, const float* x, const float* y, long long rows,
           g.N = ln.K;
           g.C = h->w_g[i & 1]; g.ldc = ln.K;
           g.aux = relu ? hbuf(h->w_h, k, i) : hbuf(h->w_d, k, i); g.ldaux = ln.K;
-          if (wide_launch_gemm<true, true, EPI_MUL_DERIV>(g, relu, 1, st)) return 1;
+          if (wide_gemm<true, true, EPI_MUL_DERIV>(h, g, relu, 1, st)) return 1;
           G = g.C;
         } else {
           g.N = D;                       // only the x part of the input carries gradient further
           g.C = h->w_u; g.ldc = D;
           g.aux = h->w_gx; g.ldaux = D;
-          if (wide_launch_gemm<true, true, EPI_ADD>(g, relu, 1, st)) return 1;
+          if (wide_gemm<true, true, EPI_ADD>(h, g, relu, 1, st)) return 1;
         }
       }
     }
@@ -580,6 +656,7 @@ int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shi
       }
     make_plan_dims_only(d, h->dims, h->plan);
     h->wide = true;
+    if (const char* e = getenv("MAFB200_WIDE_CORE")) h->wide_core = (strcmp(e, "ffma") == 0) ? 0 : 1;
   }
   if (h->wide || !make_plan(d, h->dims, h->plan2, 2) || !h->plan2.stash_all || h->plan2.R < 16) h->plan2.P = 0;
   if (const char* e = getenv("MAFB200_OCC")) h->occ_mode = atoi(e);
@@ -745,6 +822,37 @@ int mafb200_flow_elapsed(mafb200_handle h, double* total_ms, int64_t* launches) 
   }
   *total_ms = h->flow_ms_sum;
   *launches = h->flow_launches;
+  return 0;
+}
+
+// debug / test hook: one GEMM of the wide path.  variant 0: C = A[MxK] . B[KxN] (+bias 0);
+// 1: C = A[MxK] . B[NxK]^T; 2: C += A[KxM]^T . B[KxN] (split over K, mask all ones expected in `mask`).
+int mafb200_debug_gemm(int32_t variant, int32_t core, const float* A, const float* B, float* C, int32_t M,
+                       int32_t N, int32_t K, const float* zeros_n, const float* zeros_mn,
+                       const unsigned char* mask, void* stream) {
+  mafb200_handle_s fake;
+  fake.wide_core = core;
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmArgs g{};
+  g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.act = 0;
+  if (variant == 0) {
+    g.lda = K; g.ldb = N; g.ldc = N; g.bias = zeros_n;
+    return wide_gemm<true, false, EPI_BIAS>(&fake, g, true, 1, st);
+  } else if (variant == 1) {
+    g.lda = K; g.ldb = K; g.ldc = N; g.aux = zeros_mn; g.ldaux = N;
+    return wide_gemm<true, true, EPI_ADD>(&fake, g, true, 1, st);
+  } else {
+    g.lda = M; g.ldb = N; g.ldc = N; g.mask = mask;
+    const int splits = std::max(1, std::min(8, K / 256));
+    g.k_chunk = ((K + splits - 1) / splits + 31) / 32 * 32;
+    return wide_gemm<false, false, EPI_ATOMIC_MASK>(&fake, g, true, (K + g.k_chunk - 1) / g.k_chunk, st);
+  }
+}
+
+int mafb200_set_wide_core(mafb200_handle h, int32_t core) {
+  if (!h) return fail("null handle");
+  if (core != 0 && core != 1) return fail("core must be 0 (FP32 FFMA) or 1 (tcgen05 TF32)");
+  h->wide_core = core;
   return 0;
 }
 

@@ -100,6 +100,10 @@ class MafEngine:
         _lib.check(self.lib.mafb200_query(self._h, *[C.byref(a) for a in v]))
         return dict(smem_bytes=v[0].value, tile_rows=v[1].value, max_ctas=v[2].value, stash_all=v[3].value)
 
+    def set_wide_core(self, core):
+        """Wide path GEMM core: "tf32" (tcgen05, default) or "ffma" (FP32, exact)."""
+        _lib.check(self.lib.mafb200_set_wide_core(self._h, {"ffma": 0, "tf32": 1}[core]))
+
     def flow_timing(self, enable=True):
         _lib.check(self.lib.mafb200_flow_timing(self._h, 1 if enable else 0))
 

@@ -44,8 +44,10 @@ CASES = [
 
 @pytest.mark.parametrize("cfg,B,act,rev,forced", CASES)
 def test_wide_matches_oracle(cfg, B, act, rev, forced):
+    """FP32 core of the wide path: same 1e-5 tolerance as the fused narrow kernel."""
     spec, flat, std, x, y = make_case(cfg, B, seed=11, activation=act, use_reverse=rev, scale=0.05 if cfg["n_in"] == 32 else 0.12)
     eng = _engine(spec, std, forced)
+    eng.set_wide_core("ffma")
     assert eng.query()["smem_bytes"] == 0          # wide path in use
     p, xt, yt = _t(flat), _t(x), _t(y)
     f64, x64, y64 = flat.astype(np.float64), x.astype(np.float64), y.astype(np.float64)
@@ -79,6 +81,7 @@ def test_wide_equals_narrow_kernel():
     cfg = dict(n_in=8, n_cond=4, n_layers=3, layers=[64, 32])
     spec, flat, std, x, y = make_case(cfg, 513, seed=12)
     a, b = _engine(spec, std, False), _engine(spec, std, True)
+    b.set_wide_core("ffma")
     assert a.query()["smem_bytes"] > 0 and b.query()["smem_bytes"] == 0
     p, xt, yt = _t(flat), _t(x), _t(y)
     la, lb = a.log_prob(p, xt, yt), b.log_prob(p, xt, yt)
@@ -89,3 +92,57 @@ def test_wide_equals_narrow_kernel():
     b.loss_grad(p, xt, yt, l2, gb)
     assert abs(l1.item() - l2.item()) < 1e-5 * max(1, abs(l1.item()))
     assert float((ga - gb).abs().max() / ga.abs().max()) < 1e-5
+
+
+# TF32 tolerance of the tcgen05 core (operands truncated to TF32 by the tensor core, FP32 accumulate).
+# Stated bounds (measured on B200: log_prob 7e-4, loss 1.5e-4, gradient 2.4e-3 at B=4096):
+TF32_LOGP, TF32_LOSS, TF32_GRAD = 3e-3, 1e-3, 3e-2
+
+
+@pytest.mark.parametrize("cfg,B,act,rev,forced", CASES)
+def test_wide_tf32_core_within_stated_tolerance(cfg, B, act, rev, forced):
+    spec, flat, std, x, y = make_case(cfg, B, seed=11, activation=act, use_reverse=rev, scale=0.05 if cfg["n_in"] == 32 else 0.12)
+    eng = _engine(spec, std, forced)
+    eng.set_wide_core("tf32")
+    p, xt, yt = _t(flat), _t(x), _t(y)
+    f64, x64, y64 = flat.astype(np.float64), x.astype(np.float64), y.astype(np.float64)
+    lp = eng.log_prob(p, xt, yt).cpu().numpy()
+    assert rel_err(lp, onp.nde_log_prob(spec, f64, std, x64, y64)) < TF32_LOGP
+    loss, grad = torch.zeros(1, device="cuda:0"), torch.zeros_like(p)
+    eng.loss_grad(p, xt, yt, loss, grad)
+    l_ref, g_ref = onp.nll_loss_and_grad(spec, f64, std, x64, y64)
+    g = grad.cpu().numpy()
+    assert rel_err(loss.item(), l_ref) < TF32_LOSS
+    assert grad_err(g, g_ref) < TF32_GRAD
+    assert (g[spec.flat_mask() == 0] == 0).all()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(128, 128, 32), (300, 64, 160), (200, 32, 512), (128, 512, 160), (640, 512, 2048)])
+def test_tcgen05_gemm_variants(variant, shape):
+    """Raw GEMMs of the wide path: FP32 core exact to 2e-6, tcgen05 TF32 core to 2e-3 (relative to max|C|)."""
+    import ctypes as C
+    from jaxili_b200 import _lib
+    lib = _lib.load()
+    M, N, K = shape
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(variant * 100 + M)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=gen)
+    if variant == 0:
+        A, B = rnd(M, K), rnd(K, N)
+        ref = A.double() @ B.double()
+    elif variant == 1:
+        A, B = rnd(M, K), rnd(N, K)
+        ref = A.double() @ B.double().T
+    else:
+        A, B = rnd(K, M), rnd(K, N)
+        ref = A.double().T @ B.double()
+    zn, zmn = torch.zeros(N, device=dev), torch.zeros(M, N, device=dev)
+    mask = torch.ones(M, N, dtype=torch.uint8, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for core, tol in ((0, 2e-6), (1, 2e-3)):
+        out = torch.zeros(M, N, device=dev)
+        _lib.check(lib.mafb200_debug_gemm(variant, core, A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K,
+                                          zn.data_ptr(), zmn.data_ptr(), mask.data_ptr(), st))
+        torch.cuda.synchronize()
+        assert float((out.double() - ref).abs().max() / ref.abs().max()) < tol
