@@ -51,6 +51,8 @@ WORKLOADS = {
            "NLE SLCP-shaped D=8 (x), C=5 (theta), 5x[50,50], batch 16384 per GPU"),
     "c4": (dict(n_in=10, n_cond=10, n_layers=5, layers=[50, 50]), 1 << 20,
            "posterior sampling D=10,C=10, 5x[50,50]: 2^20 samples per observation per step"),
+    "c5": (dict(n_in=32, n_cond=128, n_layers=10, layers=[512, 512]), 65536,
+           "wide NPE D=32,C=128, 10x[512,512] ReLU reverse, batch 65536 per GPU, tcgen05 TF32 GEMM core"),
 }
 
 
@@ -73,6 +75,11 @@ def synth_data(name, cfg, n_rows, seed):
     """Synthetic simulator draws of the named shape, FP32."""
     rng = np.random.default_rng(seed)
     D, C = cfg["n_in"], cfg["n_cond"]
+    if name == "c5":              # theta ~ U(-1,1)^32, x = A theta + 0.3 eps, fixed A ~ N(0, 1/32)
+        theta = rng.uniform(-1, 1, size=(n_rows, D)).astype(np.float32)
+        A = np.random.default_rng(5).standard_normal((C, D)).astype(np.float32) / np.sqrt(D)
+        x = (theta @ A.T + 0.3 * rng.standard_normal((n_rows, C))).astype(np.float32)
+        return theta, x
     if name in ("c2", "c4"):      # gaussian-linear: theta ~ U(-1,1)^10, x = theta + sqrt(0.1) eps
         theta = rng.uniform(-1, 1, size=(n_rows, D)).astype(np.float32)
         x = (theta + np.sqrt(0.1) * rng.standard_normal((n_rows, C))).astype(np.float32)
@@ -264,6 +271,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W, K = max(args.warmup, 3), args.steps
+    if name == "c5" and K > 200:
+        K = 30          # a wide step is ~10 ms and 1.5 TFLOP: keep the default run within a minute
+    if name == "c4" and K > 200:
+        K = 50
 
     from jaxili_b200 import nn as bnn
     from jaxili_b200.engine import ffma_peak_tflops
@@ -357,6 +368,9 @@ def main():
         # ------------------------------------------------------------- training step
         n_batches = max(8, (168 * 2**20) // (batch * (cfg["n_in"] + cfg["n_cond"]) * 4))  # > 126 MB L2
         n_batches = min(n_batches, 512)
+        wide = name == "c5"
+        if wide:
+            n_batches = 8                                  # 8 x 65536 x 640 B = 336 MB > L2
         rows = n_batches * batch
         theta, x = synth_data(name, cfg, rows, seed=100 + rank)
         dv, cv = density_and_cond(name, theta, x)
@@ -377,7 +391,29 @@ def main():
         flops_step = train_flops_per_sample(cfg) * batch
 
         # (1) kernel-resident throughput
-        if world == 1:
+        if wide:
+            # layer-by-layer path: ~150 launches per step, batches are device-resident slices
+            state = trainer.state
+            xd, yd = trainer._batch_xy([theta_d, x_d])
+            flat = state.params.flat
+            Pn = flat.numel()
+            gbuf = trainer._gbuf
+            grad, loss = gbuf[:Pn], gbuf[-4:-3]
+            eng.pack(flat)
+            inv = 1.0 / (batch * world)
+            it_box = [0]
+
+            def step_fn():
+                i = it_box[0] % n_batches
+                it_box[0] += 1
+                eng.loss_grad(flat, xd[i * batch:(i + 1) * batch], yd[i * batch:(i + 1) * batch], loss, grad,
+                              inv_global_b=inv, packed_current=True)
+                if world > 1:
+                    dist.all_reduce(gbuf)
+                eng.clip_adam(flat, grad, state.opt_state["m"], state.opt_state["v"], state.step, state.tx,
+                              norm_current=world == 1)
+            launches_per_step = 10 * (3 + 1 + 1 + 3 * 3 + 1) + 6
+        elif world == 1:
             step_fn = trainer.make_graph_step(theta_d, x_d, batch)
             launches_per_step = 3          # flow, reduce, clip_adam
         else:
@@ -412,7 +448,7 @@ def main():
         final_loss = float(trainer._gbuf[-4].item())
 
         # (2) end to end through TrainerModule.train_step with host batches (pinned), loss read back
-        Ke = max(W, min(K, 300))
+        Ke = max(W, min(K, 10 if wide else 300))
         host_batches = [[theta[i * batch:(i + 1) * batch], x[i * batch:(i + 1) * batch]] for i in range(min(n_batches, 16))]
         for i in range(W):
             trainer.state, m = trainer.train_step(trainer.state, host_batches[i % len(host_batches)])
@@ -427,33 +463,63 @@ def main():
         ms_e = max_over_ranks(t0.elapsed_time(t1))
         e2e = Ke * batch * world / (ms_e * 1e-3)
 
-        # (3) roofline of the dominant kernel: CUDA-event bracket around the flow kernel alone
+        # (3) roofline of the dominant kernel
         xd, yd = trainer._batch_xy([theta_d, x_d])
         flat = trainer.state.params.flat
         Pn = flat.numel()
         grad, loss = trainer._gbuf[:Pn], trainer._gbuf[-4:-3]
         eng.pack(flat)
-        for _ in range(W):
+        if wide:
+            # the wide step is a chain of ~90 tcgen05 TF32 GEMM launches (+ elementwise kernels); the
+            # roofline line is the chain's tensor-pipe rate: CUDA events around loss_grad
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            Kr = min(K, 10)
+            r0.record()
+            for i in range(Kr):
+                j = i % n_batches
+                eng.loss_grad(flat, xd[j * batch:(j + 1) * batch], yd[j * batch:(j + 1) * batch], loss, grad,
+                              packed_current=True)
+            r1.record()
+            torch.cuda.synchronize(dev)
+            kernel_ms = r0.elapsed_time(r1) / Kr
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    mp = json.load(f)
+                peak_tc, src = mp["bf16_tflops_sustained"] / 2, "half of MEASURED_PEAKS.json bf16_tflops_sustained (no TF32 entry)"
+            except Exception:
+                peak_tc, src = 1590.0 / 2, "half of the fallback bf16 figure (1.59 PFLOP/s)"
+            achieved = flops_step / (kernel_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": achieved, "peak": peak_tc, "unit": "TFLOP/s",
+                    "frac": achieved / peak_tc, "traffic": None, "kernel": "wide_tc_gemm_kernel chain (loss_grad)",
+                    "kernel_us": kernel_ms * 1e3, "flops_per_launch": flops_step, "peak_source": src,
+                    "dtype_note": "TF32 operands (tensor core truncation), FP32 accumulate; tolerance in DESIGN.md"}
+        for _ in range(0 if wide else W):
             eng.loss_grad(flat, xd, yd, loss, grad, batch_rows=batch, batch_index=trainer.state.step,
                           n_batches=n_batches, packed_current=True)
         torch.cuda.synchronize(dev)
-        eng.flow_timing(True)
-        Kr = min(K, 300)
-        for i in range(Kr):
-            trainer.state.step.add_(1)     # walk through the dataset (> L2) as the training loop does
-            eng.loss_grad(flat, xd, yd, loss, grad, batch_rows=batch, batch_index=trainer.state.step,
-                          n_batches=n_batches, packed_current=True)
-        tot_ms, n_l = eng.flow_elapsed()
-        eng.flow_timing(False)
-        kernel_ms = tot_ms / max(n_l, 1)
-        peak = ffma_peak_tflops(local)
-        achieved = flops_step / (kernel_ms * 1e-3) / 1e12
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(name)
-        except Exception:
-            pass
+        if not wide:
+            eng.flow_timing(True)
+            Kr = min(K, 300)
+            for i in range(Kr):
+                trainer.state.step.add_(1)     # walk through the dataset (> L2) as the training loop does
+                eng.loss_grad(flat, xd, yd, loss, grad, batch_rows=batch, batch_index=trainer.state.step,
+                              n_batches=n_batches, packed_current=True)
+            tot_ms, n_l = eng.flow_elapsed()
+            eng.flow_timing(False)
+            kernel_ms = tot_ms / max(n_l, 1)
+            peak = ffma_peak_tflops(local)
+            achieved = flops_step / (kernel_ms * 1e-3) / 1e12
+            traffic = None
+            try:
+                with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                    traffic = json.load(f).get(name)
+            except Exception:
+                pass
+            roof = {"bound": "fp32_ffma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": traffic, "kernel": "maf_flow_kernel<BWD>",
+                    "kernel_us": kernel_ms * 1e3, "flops_per_launch": flops_step,
+                    "peak_source": "FFMA micro-benchmark run live (MEASURED_PEAKS.json has no FP32 entry); "
+                                   "nominal 74.5 TFLOP/s"}
         out = {
             "metric": "MAF train samples/sec (fwd+bwd+clip+Adam)", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
@@ -467,13 +533,12 @@ def main():
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": batch * (cfg["n_in"] + cfg["n_cond"]) * 4,
                     "d2h_bytes_per_step": 4, "steps": Ke},
             "gpu_launches": launches_per_step * K,
-            "roofline": {"bound": "fp32_ffma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": traffic, "kernel": "maf_flow_kernel<BWD>",
-                         "kernel_us": kernel_ms * 1e3, "flops_per_launch": flops_step,
-                         "peak_source": "FFMA micro-benchmark run live (MEASURED_PEAKS.json has no FP32 entry); "
-                                        "nominal 74.5 TFLOP/s"},
+            "roofline": roof,
             "clocks": clk,
         }
+        if wide:
+            out["dtype"] = "tf32"
+            out["config"]["l2"] = "8 resident batches x 40 MiB, activations (GBs per step) stream through HBM"
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
@@ -482,9 +547,10 @@ def main():
             out["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
                                    "sample": f"20000 samples of one observation in {dt:.1f} s (oracle/maf_torch.py)"}
         else:
-            v, n, dt = cpu_train_throughput(name, cfg, batch, 12.0, threads)
+            cb = batch if name != "c5" else 4096
+            v, n, dt = cpu_train_throughput(name, cfg, cb, 12.0, threads)
             out["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-                                   "sample": f"{n} train steps of batch {batch} in {dt:.1f} s (oracle/maf_torch.py)"}
+                                   "sample": f"{n} train steps of batch {cb} in {dt:.1f} s (oracle/maf_torch.py)"}
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -20,3 +20,4 @@ def run(variant, core, M, N, K, structured=False):
     return f"{err:.2e}"
 for (M, N, K) in [(128, 128, 32), (128, 128, 64), (128, 128, 512), (256, 256, 96), (300, 64, 160), (200, 32, 512), (128, 512, 160)]:
     print((M, N, K), {v: {c: run(v, c, M, N, K) for c in (0, 1)} for v in (0, 1, 2)}, flush=True)
+print("big K:", {v: run(v, 1, 640, 512, 2048) for v in (0, 1, 2)}, {v: run(v, 1, 640, 512, 8192) for v in (0, 1, 2)})

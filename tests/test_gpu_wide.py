@@ -140,7 +140,7 @@ def test_tcgen05_gemm_variants(variant, shape):
     zn, zmn = torch.zeros(N, device=dev), torch.zeros(M, N, device=dev)
     mask = torch.ones(M, N, dtype=torch.uint8, device=dev)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    for core, tol in ((0, 2e-6), (1, 2e-3)):
+    for core, tol in ((0, 2e-6 if K <= 512 else 1e-5), (1, 2e-3)):
         out = torch.zeros(M, N, device=dev)
         _lib.check(lib.mafb200_debug_gemm(variant, core, A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K,
                                           zn.data_ptr(), zmn.data_ptr(), mask.data_ptr(), st))
