@@ -411,27 +411,29 @@ template <bool A_MN, bool B_MN, int EPI>
 int wide_launch_tc(const GemmArgs& g, bool relu, int splits, cudaStream_t st) {
   CUtensorMap ta, tb;
   // K-major: inner = reduction (g.K), outer = output rows; MN-major: inner = output, outer = reduction
-  if (A_MN ? make_tmap(&ta, g.A, g.M, g.K, g.lda, 32, 32, true) : make_tmap(&ta, g.A, g.K, g.M, g.lda, 32, TC_BM, false))
-    return 1;
-#define WTC(BN_)                                                                                           \
+#define WTC(BM_, BN_)                                                                                      \
   do {                                                                                                     \
+    if (A_MN ? make_tmap(&ta, g.A, g.M, g.K, g.lda, 32, 32, true) : make_tmap(&ta, g.A, g.K, g.M, g.lda, 32, 128, false)) \
+      return 1;                                                                                            \
     if (B_MN ? make_tmap(&tb, g.B, g.N, g.K, g.ldb, 32, 32, true) : make_tmap(&tb, g.B, g.K, g.N, g.ldb, 32, BN_, false)) \
       return 1;                                                                                            \
-    const dim3 grid((g.N + BN_ - 1) / BN_, (g.M + TC_BM - 1) / TC_BM, splits);                             \
+    using Cfg = TcCfg<BM_, BN_>;                                                                           \
+    const dim3 grid((g.N + BN_ - 1) / BN_, (g.M + BM_ - 1) / BM_, splits);                                 \
     static bool attr_t = false, attr_f = false;                                                            \
     if (relu) {                                                                                            \
-      auto kfn = wide_tc_gemm_kernel<BN_, A_MN, B_MN, EPI, true>;                                          \
-      if (!attr_t) { CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN_>::SMEM_BYTES)); attr_t = true; } \
-      kfn<<<grid, 192, TcCfg<BN_>::SMEM_BYTES, st>>>(ta, tb, g);                                           \
+      auto kfn = wide_tc_gemm_kernel<BM_, BN_, A_MN, B_MN, EPI, true>;                                     \
+      if (!attr_t) { CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); attr_t = true; } \
+      kfn<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, g);                                         \
     } else {                                                                                               \
-      auto kfn = wide_tc_gemm_kernel<BN_, A_MN, B_MN, EPI, false>;                                         \
-      if (!attr_f) { CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN_>::SMEM_BYTES)); attr_f = true; } \
-      kfn<<<grid, 192, TcCfg<BN_>::SMEM_BYTES, st>>>(ta, tb, g);                                           \
+      auto kfn = wide_tc_gemm_kernel<BM_, BN_, A_MN, B_MN, EPI, false>;                                    \
+      if (!attr_f) { CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); attr_f = true; } \
+      kfn<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, g);                                         \
     }                                                                                                      \
   } while (0)
-  if (g.N > 64) WTC(128);
-  else if (g.N > 32) WTC(64);
-  else WTC(32);
+  if (g.N >= 256 && g.M >= 256) WTC(256, 256);
+  else if (g.N > 64) WTC(128, 128);
+  else if (g.N > 32) WTC(128, 64);
+  else WTC(128, 32);
 #undef WTC
   CU(cudaGetLastError());
   return 0;

@@ -88,21 +88,27 @@ __host__ __device__ constexpr uint32_t tc_instr_desc(int M, int N, bool a_mn, bo
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN>
+template <int BM, int BN>
 struct TcCfg {
-  static constexpr int STAGES = BN >= 128 ? 3 : 4;
-  static constexpr int A_BYTES = TC_BM * TC_BK * 4;     // 16 KB
+  static constexpr int MH = BM / 128;                   // 128-row halves, one MMA + accumulator each
+  static constexpr int STAGES = (BM * BN >= 256 * 256) ? 3 : (BN >= 128 ? 3 : 4);
+  static constexpr int A_BYTES = BM * TC_BK * 4;        // 16 KB per half
   static constexpr int B_BYTES = BN * TC_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int THREADS = 64 + 128 * MH;         // TMA warp, MMA warp, 4 epilogue warps per half
+  static constexpr int TMEM_COLS = MH * BN;             // power of two in {32, ..., 512}
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool RELU>
-__global__ void __launch_bounds__(192)
+// Tile BM x BN per CTA, BM in {128, 256}.  BM = 256 runs two M=128 MMAs per k-step against the same
+// B tile (32 MAC per operand byte instead of 16: with 4-byte TF32 operands the 128x128 tile is
+// L2-bandwidth-bound), its two accumulators fill all 512 TMEM columns.
+template <int BM, int BN, bool A_MN, bool B_MN, int EPI, bool RELU>
+__global__ void __launch_bounds__(TcCfg<BM, BN>::THREADS)
 wide_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ GemmArgs g) {
-  using Cfg = TcCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  using Cfg = TcCfg<BM, BN>;
+  constexpr int STAGES = Cfg::STAGES, MH = Cfg::MH;
   extern __shared__ unsigned char tc_smem_raw[];
   unsigned char* tiles = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -112,7 +118,7 @@ wide_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   int k_begin = 0, k_end = g.K;
   if (EPI == EPI_ATOMIC_MASK) {
     k_begin = blockIdx.z * g.k_chunk;
@@ -128,9 +134,9 @@ wide_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     mbar_init(accum_full, 1);
     mbar_fence_init();
   }
-  if (warp == 1) {   // TMEM: BN FP32 accumulator columns
+  if (warp == 1) {   // TMEM: MH accumulators of BN FP32 columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(BN));
+                 "n"(Cfg::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -150,9 +156,10 @@ wide_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
         if (A_MN) {
 #pragma unroll
-          for (int a = 0; a < TC_BM / 32; ++a) tma_load_2d(a_dst + a * 4096, &tmA, m0 + 32 * a, k0, &full[s]);
+          for (int a = 0; a < BM / 32; ++a) tma_load_2d(a_dst + a * 4096, &tmA, m0 + 32 * a, k0, &full[s]);
         } else {
-          tma_load_2d(a_dst, &tmA, k0, m0, &full[s]);
+#pragma unroll
+          for (int hh = 0; hh < MH; ++hh) tma_load_2d(a_dst + hh * 16384, &tmA, k0, m0 + 128 * hh, &full[s]);
         }
         if (B_MN) {
 #pragma unroll
@@ -165,7 +172,7 @@ wide_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = tc_instr_desc(TC_BM, BN, A_MN, B_MN);
+      constexpr uint32_t idesc = tc_instr_desc(128, BN, A_MN, B_MN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         mbar_wait(&full[s], (uint32_t)((kb / STAGES) & 1));
@@ -176,74 +183,91 @@ wide_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int k = 0; k < TC_BK / 8; ++k) {
           // K-major: step 8 floats (32 B) inside the swizzled 128-B row; 8-row groups 1024 B apart.
           // MN-major: step 8 k-rows (1024 B) = two 4-row groups 512 B apart; 32-wide MN atoms 4096 B apart.
-          const uint64_t ad = A_MN ? tc_smem_desc(a_addr + k * 1024, 4096, 512, 1)
-                                   : tc_smem_desc(a_addr + k * 32, 16, 1024, 2);
           const uint64_t bd = B_MN ? tc_smem_desc(b_addr + k * 1024, 4096, 512, 1)
                                    : tc_smem_desc(b_addr + k * 32, 16, 1024, 2);
-          tc_mma_tf32(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+#pragma unroll
+          for (int hh = 0; hh < MH; ++hh) {
+            const uint32_t ah = a_addr + hh * 16384;   // 128 rows of A: 16 KB in either layout
+            const uint64_t ad = A_MN ? tc_smem_desc(ah + k * 1024, 4096, 512, 1)
+                                     : tc_smem_desc(ah + k * 32, 16, 1024, 2);
+            tc_mma_tf32(tmem_base + hh * BN, ad, bd, idesc, (kb | k) ? 1u : 0u);
+          }
         }
         tc_commit(&empty[s]);          // smem slot reusable once these MMAs have read it
       }
-      tc_commit(accum_full);           // accumulator complete
+      tc_commit(accum_full);           // accumulators complete
     }
   } else {
-    // ===== epilogue warps: TMEM lane group = warp % 4
+    // ===== epilogue warps: TMEM lane group = warp % 4, accumulator half = (warp - 2) / 4.
+    // tcgen05.ld hands every lane one accumulator ROW; each 32x32 chunk is transposed through shared
+    // memory (the pipeline buffers are drained once the accumulator barrier fires) so that global
+    // loads / stores / reductions are coalesced 128-byte row segments.
     mbar_wait(accum_full, 0);
     tc_fence_after();
     const int lg = warp & 3;
-    const int m = m0 + lg * 32 + lane;
+    const int hh = (warp - 2) >> 2;
+    const int m_base = m0 + hh * 128 + lg * 32;
+    float* stg = reinterpret_cast<float*>(tiles) + (warp - 2) * (32 * 33);
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       float v[32];
-      if (num_kb > 0) tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + c, v);
+      if (num_kb > 0) tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + hh * BN + c, v);
       else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      if (m < g.M) {
-        const int nb = n0 + c;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+      __syncwarp();
+      const int n = n0 + c + lane;
+      if (n < g.N) {
+        float bn = 0.f;
+        if (EPI == EPI_BIAS_ACT || EPI == EPI_BIAS) bn = g.bias[n];
+        const int rows = min(32, g.M - m_base);
+        // all 32 row-segment loads of the chunk are issued before any is used (memory-level parallelism)
+        float a[32];
+        if (EPI == EPI_MUL_DERIV || EPI == EPI_ADD) {
+          const float* ap = g.aux + (size_t)m_base * g.ldaux + n;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) a[r] = r < rows ? ap[(size_t)r * g.ldaux] : 0.f;
+        }
         if (EPI == EPI_ATOMIC_MASK) {
-          float* crow = g.C + (size_t)m * g.ldc + nb;
-          const unsigned char* mrow = g.mask + (size_t)m * g.N + nb;
+          const unsigned char* mp = g.mask + (size_t)m_base * g.N + n;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < g.N && mrow[j]) atomicAdd(crow + j, v[j]);
-        } else {
-          float* crow = g.C + (size_t)m * g.ldc + nb;
+          for (int r = 0; r < 32; ++r) a[r] = (r < rows && mp[(size_t)r * g.N]) ? 1.f : 0.f;
+        }
+        float* cp = g.C + (size_t)m_base * g.ldc + n;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (nb + j >= g.N) break;
-            float o[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int n = nb + j + q;
-              float r = v[j + q];
-              if (EPI == EPI_BIAS_ACT) {
-                float hh, dd;
-                act_eval<RELU>(g.act, r + g.bias[n], hh, dd);
-                r = hh;
-                if (!RELU && g.aux_out) g.aux_out[(size_t)m * g.ldaux_out + n] = dd;
-              } else if (EPI == EPI_BIAS) {
-                r = r + g.bias[n];
-              } else if (EPI == EPI_MUL_DERIV) {
-                const float a = g.aux[(size_t)m * g.ldaux + n];
-                r = RELU ? (a > 0.f ? r : 0.f) : r * a;
-              } else if (EPI == EPI_ADD) {
-                r = r + g.aux[(size_t)m * g.ldaux + n];
-              }
-              o[q] = r;
+        for (int r = 0; r < 32; ++r) {
+          float val = stg[r * 33 + lane];
+          if (EPI == EPI_ATOMIC_MASK) {
+            if (a[r] != 0.f)
+              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(cp + (size_t)r * g.ldc), "f"(val) : "memory");
+          } else if (r < rows) {
+            if (EPI == EPI_BIAS_ACT) {
+              float hv, dd;
+              act_eval<RELU>(g.act, val + bn, hv, dd);
+              val = hv;
+              if (!RELU && g.aux_out) g.aux_out[(size_t)(m_base + r) * g.ldaux_out + n] = dd;
+            } else if (EPI == EPI_BIAS) {
+              val = val + bn;
+            } else if (EPI == EPI_MUL_DERIV) {
+              val = RELU ? (a[r] > 0.f ? val : 0.f) : val * a[r];
+            } else if (EPI == EPI_ADD) {
+              val = val + a[r];
             }
-            *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);   // N % 4 == 0
+            cp[(size_t)r * g.ldc] = val;
           }
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
   }
 }
 
