@@ -532,10 +532,12 @@ int wide_chunk(mafb200_handle h, const float* x, const float* y, long long rows,
         g.mask = ml + ln.pw_off;
         g.k_chunk = k_chunk;
         if (wide_gemm<false, false, EPI_ATOMIC_MASK>(h, g, relu, (int)((rows + k_chunk - 1) / k_chunk), st)) return 1;
-        const int rpb = 512;
-        wide_colsum_kernel<<<dim3((ln.N + 127) / 128, (unsigned)((rows + rpb - 1) / rpb)), 128, 0, st>>>(
-            G, rows, ln.N, rpb, gl + ln.pb_off);
-        CU(cudaGetLastError());
+        if (i == n_lin - 1) {   // hidden levels get their bias gradient from the producing GEMM's epilogue
+          const int rpb = 512;
+          wide_colsum_kernel<<<dim3((ln.N + 127) / 128, (unsigned)((rows + rpb - 1) / rpb)), 128, 0, st>>>(
+              G, rows, ln.N, rpb, gl + ln.pb_off);
+          CU(cudaGetLastError());
+        }
       }
       {  // input gradient
         GemmArgs g{};
@@ -547,6 +549,7 @@ int wide_chunk(mafb200_handle h, const float* x, const float* y, long long rows,
           g.N = ln.K;
           g.C = h->w_g[i & 1]; g.ldc = ln.K;
           g.aux = relu ? hbuf(h->w_h, k, i) : hbuf(h->w_d, k, i); g.ldaux = ln.K;
+          g.colsum = gl + P.lin[i - 1].pb_off;      // db_{i-1} = column sums of g_a_{i-1}
           if (wide_gemm<true, true, EPI_MUL_DERIV>(h, g, relu, 1, st)) return 1;
           G = g.C;
         } else {

@@ -28,6 +28,8 @@ struct GemmArgs {
   const unsigned char* mask;    // EPI_ATOMIC_MASK: [M x N] (ld = N)
   int act;
   int k_chunk;                  // TN: reduction rows per CTA (split-K over blockIdx.z)
+  float* colsum;                // optional [N]: column sums of the OUTPUT accumulate here (bias gradient
+                                // of the previous linear, fused into the input-gradient product)
 };
 
 // 128 x BN x 8 tiles, 256 threads, 8 x (BN/16) outputs per thread, register-prefetched double buffer.
@@ -170,6 +172,9 @@ __global__ void __launch_bounds__(256) wide_gemm_kernel(const __grid_constant__ 
   }
 
   // ---- fused epilogue
+  float csum[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) csum[j] = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int m = m0 + tm + i;
@@ -188,13 +193,20 @@ __global__ void __launch_bounds__(256) wide_gemm_kernel(const __grid_constant__ 
         g.C[(size_t)m * g.ldc + n] = v + g.bias[n];
       } else if (EPI == EPI_MUL_DERIV) {
         const float a = g.aux[(size_t)m * g.ldaux + n];
-        g.C[(size_t)m * g.ldc + n] = RELU ? (a > 0.f ? v : 0.f) : v * a;
+        const float o = RELU ? (a > 0.f ? v : 0.f) : v * a;
+        g.C[(size_t)m * g.ldc + n] = o;
+        if (g.colsum) csum[j] += o;
       } else if (EPI == EPI_ADD) {
         g.C[(size_t)m * g.ldc + n] = v + g.aux[(size_t)m * g.ldaux + n];
       } else {   // EPI_ATOMIC_MASK: masked weight gradient, rows split over blockIdx.z
         if (g.mask[(size_t)m * g.N + n]) atomicAdd(&g.C[(size_t)m * g.ldc + n], v);
       }
     }
+  }
+  if (EPI == EPI_MUL_DERIV && g.colsum) {
+#pragma unroll
+    for (int j = 0; j < TN; ++j)
+      if (n0 + tn + j < g.N) atomicAdd(&g.colsum[n0 + tn + j], csum[j]);
   }
 }
 

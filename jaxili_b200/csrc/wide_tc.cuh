@@ -208,8 +208,10 @@ wide_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int hh = (warp - 2) >> 2;
     const int m_base = m0 + hh * 128 + lg * 32;
     float* stg = reinterpret_cast<float*>(tiles) + (warp - 2) * (32 * 33);
+    float* csm = reinterpret_cast<float*>(tiles) + 8 * (32 * 33);      // [4 * MH warps][BN] column sums
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
+      float csum = 0.f;
       float v[32];
       if (num_kb > 0) tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + hh * BN + c, v);
       else {
@@ -253,6 +255,7 @@ wide_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               val = val + bn;
             } else if (EPI == EPI_MUL_DERIV) {
               val = RELU ? (a[r] > 0.f ? val : 0.f) : val * a[r];
+              csum += val;
             } else if (EPI == EPI_ADD) {
               val = val + a[r];
             }
@@ -260,7 +263,19 @@ wide_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+      if (EPI == EPI_MUL_DERIV && g.colsum) csm[(warp - 2) * BN + c + lane] = csum;
       __syncwarp();
+    }
+    if (EPI == EPI_MUL_DERIV && g.colsum) {
+      // bias gradient of the previous linear = column sums of this output: combine the CTA's
+      // epilogue warps in shared memory, then one coalesced reduction per column
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * MH));
+      for (int cc = (warp - 2) * 32 + lane; cc < BN; cc += 128 * MH) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4 * MH; ++w) t += csm[w * BN + cc];
+        if (n0 + cc < g.N) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(g.colsum + n0 + cc), "f"(t) : "memory");
+      }
     }
   }
   tc_fence_before();
