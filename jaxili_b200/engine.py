@@ -74,13 +74,13 @@ class MafEngine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _chk(self, t, name, cols=None):
+    def _chk(self, t, name, cols=None, align=16):
         if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise TypeError(f"{name} must be a contiguous float32 CUDA tensor")
         if t.device != self.device:
             raise ValueError(f"{name} is on {t.device}, engine is on {self.device}")
-        if t.data_ptr() % 16:
-            raise ValueError(f"{name} must be 16-byte aligned")
+        if t.data_ptr() % align:
+            raise ValueError(f"{name} must be {align}-byte aligned")
         if cols is not None and (t.dim() != 2 or t.shape[1] != cols):
             raise ValueError(f"{name} must have shape (rows, {cols}), got {tuple(t.shape)}")
         return C.c_void_p(t.data_ptr())
@@ -210,7 +210,7 @@ class MafEngine:
         if N:
             _lib.check(self.lib.mafb200_sample_from_noise(
                 self._h, self._chk(params, "params"), pu,
-                self._chk(y_obs, "y_obs") if self.n_cond else None, n_obs, int(rows_per_obs), N,
+                self._chk(y_obs, "y_obs", align=4) if self.n_cond else None, n_obs, int(rows_per_obs), N,
                 self._chk(out, "out"), _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
         return out
 
@@ -225,7 +225,7 @@ class MafEngine:
         if N:
             _lib.check(self.lib.mafb200_sample_philox(
                 self._h, self._chk(params, "params"), int(seed) & (2**64 - 1), int(row_offset),
-                self._chk(y_obs, "y_obs") if self.n_cond else None, n_obs, int(rows_per_obs), int(N),
+                self._chk(y_obs, "y_obs", align=4) if self.n_cond else None, n_obs, int(rows_per_obs), int(N),
                 self._chk(out, "out"), _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
         return out
 
