@@ -312,6 +312,10 @@ class TrainerModule:
         """CUDA-graph replay of one whole step over a GPU-resident dataset: the batch is selected on
         the device from the optax step counter, so one graph launch = forward + backward + reduction
         + clip + Adam with no host work.  Returns ``step() -> None`` (loss in ``self.last_loss``)."""
+        if parallel.world_info()[1] > 1:
+            # capturing the NCCL all-reduce together with the kernels hung on 2xB200 (torch 2.11 /
+            # NCCL 2.28.9); multi-rank steps are launched eagerly (TrainerModule.train_step)
+            raise NotImplementedError("make_graph_step is single-process; use train_step under torch.distributed")
         state = self.state
         eng = self.model.engine()
         xd, yd = self._batch_xy([theta_dev, x_dev])
