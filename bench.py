@@ -426,12 +426,19 @@ def main():
             eng.pack(flat)
             inv = 1.0 / (batch * world)
 
-            def step_fn():
-                eng.loss_grad(flat, xd, yd, loss, grad, batch_rows=batch, inv_global_b=inv, batch_index=state.step,
-                              n_batches=n_batches, packed_current=True)
-                dist.all_reduce(gbuf)
-                eng.clip_adam(flat, grad, state.opt_state["m"], state.opt_state["v"], state.step, state.tx)
-            launches_per_step = 4          # flow, reduce, sqnorm, clip_adam (+ NCCL's own kernel)
+            from jaxili_b200 import parallel
+            peer = (not os.environ.get("MAFB200_NO_PEER")) and parallel.setup_peer_allreduce(eng, state.step)
+            if peer:
+                # one-shot all-reduce over NVLink peer memory fused with the norm partials; no NCCL call
+                # is left in the step, so the whole step is one CUDA graph like the single-GPU case
+                step_fn = trainer.make_graph_step(theta_d, x_d, batch)
+            else:
+                def step_fn():
+                    eng.loss_grad(flat, xd, yd, loss, grad, batch_rows=batch, inv_global_b=inv,
+                                  batch_index=state.step, n_batches=n_batches, packed_current=True)
+                    dist.all_reduce(gbuf)
+                    eng.clip_adam(flat, grad, state.opt_state["m"], state.opt_state["v"], state.step, state.tx)
+            launches_per_step = 4          # flow, reduce, all-reduce (own kernel or sqnorm + NCCL's), clip_adam
         for _ in range(W):
             step_fn()
         barrier_sync()
@@ -529,7 +536,8 @@ def main():
                        "l2": f"resident dataset {rows * (cfg['n_in'] + cfg['n_cond']) * 4 / 2**20:.0f} MiB > 126 MB L2, "
                              "batches walked by the on-device step counter",
                        "optimizer": "clip_by_global_norm(5) + adam(warmup_cosine(5e-4))",
-                       "parallelism": f"dp{world}", "final_loss": final_loss},
+                       "parallelism": f"dp{world}", "final_loss": final_loss,
+                       "allreduce": ("none" if world == 1 else ("nccl" if wide or not peer else "peer-memory one-shot (own kernel)"))},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": batch * (cfg["n_in"] + cfg["n_cond"]) * 4,
                     "d2h_bytes_per_step": 4, "steps": Ke},
             "gpu_launches": launches_per_step * K,

@@ -67,7 +67,10 @@ enum {
   /* clip_adam: the handle's squared-norm partials already describe `grad` (true right
      after loss_grad on the same handle when grad was not modified, e.g. no all-reduce):
      skip the norm launch. */
-  MAFB200_NORM_CURRENT = 2
+  MAFB200_NORM_CURRENT = 2,
+  /* loss_grad: write the reduced gradient and loss into this rank's symmetric (peer-mapped) slot
+     instead of out_grad / out_loss; mafb200_dp_allreduce then sums the ranks' slots. */
+  MAFB200_DP_SLOT = 4
 };
 
 typedef struct mafb200_handle_s* mafb200_handle;
@@ -123,6 +126,22 @@ int mafb200_debug_trace(mafb200_handle h, long long* trace_dev);
    under CUDA-graph capture. */
 int mafb200_flow_timing(mafb200_handle h, int32_t enable);
 int mafb200_flow_elapsed(mafb200_handle h, double* total_ms, int64_t* launches);
+
+/* Data parallel over NVLink peer memory (one process per GPU, at most 8 ranks of one node).
+   dp_init allocates this rank's symmetric buffer and returns its 64-byte CUDA IPC handle; the host
+   exchanges handles (e.g. torch.distributed.all_gather) and passes all of them, rank-major, to
+   dp_connect; dp_bind_step names the device step counter (the exchange epoch and the slot parity are
+   derived from it on the device, so the whole step is CUDA-graph capturable).
+   Per step: loss_grad(..., MAFB200_DP_SLOT) -> dp_allreduce -> clip_adam(..., MAFB200_NORM_CURRENT).
+   dp_allreduce is a one-shot all-reduce (every rank reads every peer's slot) in a fixed rank order, so
+   replicas stay bit-identical; it replaces ncclAllReduce for this latency-bound message.  Every rank
+   must call it the same number of times.  dp_error reports a peer time-out (synchronises). */
+int mafb200_dp_init(mafb200_handle h, int32_t rank, int32_t world, void* ipc_handle_out);
+int mafb200_dp_connect(mafb200_handle h, const void* all_handles);
+int mafb200_dp_bind_step(mafb200_handle h, const int32_t* step);   /* device optax count = exchange epoch - 1 */
+int mafb200_dp_reset(mafb200_handle h);   /* all ranks, between host barriers, when the count restarts */
+int mafb200_dp_allreduce(mafb200_handle h, float* grad_out, float* loss_out, void* stream);
+int mafb200_dp_error(mafb200_handle h, int32_t* out);
 
 /* Models whose MADE does not fit shared memory run layer by layer ("wide" path).  Its GEMM core is
    tcgen05 TF32 (core = 1, default; FP32 accumulate, operands truncated to TF32: log_prob agrees

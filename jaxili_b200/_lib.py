@@ -22,6 +22,7 @@ ACTIVATIONS = {
 
 PACKED_CURRENT = 1
 NORM_CURRENT = 2
+DP_SLOT = 4
 
 
 class MafDesc(C.Structure):
@@ -52,6 +53,12 @@ SYMBOLS = {
     "mafb200_debug_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mafb200_flow_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "mafb200_flow_elapsed": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "mafb200_dp_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "mafb200_dp_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mafb200_dp_bind_step": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mafb200_dp_reset": (C.c_int, [C.c_void_p]),
+    "mafb200_dp_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mafb200_dp_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "mafb200_debug_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                      C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mafb200_set_wide_core": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -13,6 +13,7 @@
 #include "flow_kernel.cuh"
 #include "opt_kernels.cuh"
 #include "sample_kernel.cuh"
+#include "dp_kernel.cuh"
 #include "wide_kernels.cuh"
 #include "wide_tc.cuh"
 
@@ -65,6 +66,13 @@ struct mafb200_handle_s {
   float logdet_const = 0.f;
   int n_norm = 0;
   long long* trace = nullptr;   // debug: device buffer of 1001 int64 (set by mafb200_debug_trace)
+  // data parallel over NVLink peer memory (dp_kernel.cuh)
+  int dp_rank = -1, dp_world = 0;
+  const int* dp_step = nullptr;                    // device optax count shared by the step's kernels
+  float* dp_sym = nullptr;                         // own: [2][r4(P) + 4] gradient slots, then flags
+  unsigned int* dp_flags = nullptr;                // own flag array (inside dp_sym allocation)
+  float* dp_peer_sym[DP_MAX_WORLD] = {};           // mapped peers (own pointer at [rank])
+  unsigned int* dp_error = nullptr;
   // wide (layer-by-layer) path: used when the MADE does not fit shared memory
   bool wide = false;
   int wide_core = 1;            // 1: tcgen05 TF32 GEMM core, 0: FP32 FFMA core (exact)
@@ -306,6 +314,8 @@ bool make_sample_plan(const MafDesc& d, const int* dims, SamplePlan& S) {
 }
 
 }  // namespace
+
+static size_t dp_slot_floats(const Plan& P) { return (size_t)((P.P + 3) & ~3) + 4; }
 
 template <bool BWD>
 static void launch_flow(const Plan& P, const FlowArgs& A, int grid, cudaStream_t st) {
@@ -785,6 +795,10 @@ int mafb200_destroy(mafb200_handle h) {
   cudaFree(h->partial_loss);
   cudaFree(h->normpart);
   cudaFree(h->done_counter);
+  for (int r = 0; r < h->dp_world; ++r)
+    if (r != h->dp_rank && h->dp_peer_sym[r]) cudaIpcCloseMemHandle(h->dp_peer_sym[r]);
+  cudaFree(h->dp_sym);
+  cudaFree(h->dp_error);
   cudaFree(h->wm);
   cudaFree(h->w_a0); cudaFree(h->w_h); cudaFree(h->w_d); cudaFree(h->w_s); cudaFree(h->w_v);
   cudaFree(h->w_o); cudaFree(h->w_u); cudaFree(h->w_gx); cudaFree(h->w_ld);
@@ -852,6 +866,102 @@ int mafb200_debug_gemm(int32_t variant, int32_t core, const float* A, const floa
     g.k_chunk = ((K + splits - 1) / splits + 31) / 32 * 32;
     return wide_gemm<false, false, EPI_ATOMIC_MASK>(&fake, g, true, (K + g.k_chunk - 1) / g.k_chunk, st);
   }
+}
+
+// ---- data parallel over peer memory ------------------------------------------------------------
+
+int mafb200_dp_init(mafb200_handle h, int32_t rank, int32_t world, void* ipc_handle_out) {
+  if (!h || !ipc_handle_out) return fail("null argument");
+  if (world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world) return fail("bad rank / world (max 8)");
+  if (h->dp_sym) return fail("dp already initialised");
+  CU(cudaSetDevice(h->device));
+  const size_t bytes = 2 * dp_slot_floats(h->plan) * 4 + DP_MAX_WORLD * sizeof(unsigned int);
+  CU(cudaMalloc(&h->dp_sym, bytes));
+  CU(cudaMemset(h->dp_sym, 0, bytes));
+  CU(cudaMalloc(&h->dp_error, 4));
+  CU(cudaMemset(h->dp_error, 0, 4));
+  h->dp_flags = reinterpret_cast<unsigned int*>(h->dp_sym + 2 * dp_slot_floats(h->plan));
+  h->dp_rank = rank;
+  h->dp_world = world;
+  h->dp_peer_sym[rank] = h->dp_sym;
+  cudaIpcMemHandle_t hd;
+  CU(cudaIpcGetMemHandle(&hd, h->dp_sym));
+  static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(ipc_handle_out, &hd, sizeof(hd));
+  return 0;
+}
+
+int mafb200_dp_connect(mafb200_handle h, const void* all_handles) {
+  if (!h || !all_handles || !h->dp_sym) return fail("dp not initialised");
+  CU(cudaSetDevice(h->device));
+  for (int r = 0; r < h->dp_world; ++r) {
+    if (r == h->dp_rank) continue;
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, static_cast<const char*>(all_handles) + 64 * r, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->dp_peer_sym[r] = static_cast<float*>(p);
+  }
+  return 0;
+}
+
+// sums the ranks' reduced gradients (written by mafb200_loss_grad with MAFB200_DP_SLOT) into
+// grad_out / loss_out and leaves the squared-norm partials current for mafb200_clip_adam
+int mafb200_dp_allreduce(mafb200_handle h, float* grad_out, float* loss_out, void* stream) {
+  if (!h || !grad_out || !loss_out) return fail("null argument");
+  if (!h->dp_sym) return fail("dp not initialised");
+  for (int r = 0; r < h->dp_world; ++r)
+    if (!h->dp_peer_sym[r]) return fail("dp peers not connected");
+  if (!h->dp_step) return fail("mafb200_dp_bind_step was not called");
+  const Plan& P = h->plan;
+  DpArgs a{};
+  a.rank = h->dp_rank;
+  a.world = h->dp_world;
+  a.P = P.P;
+  a.step = h->dp_step;
+  const size_t sf = dp_slot_floats(P);
+  a.slot_floats = (long long)sf;
+  for (int r = 0; r < h->dp_world; ++r) {
+    a.sym[r] = h->dp_peer_sym[r];
+    a.flags_of[r] = reinterpret_cast<unsigned int*>(h->dp_peer_sym[r] + 2 * sf);
+  }
+  a.grad_out = grad_out;
+  a.loss_out = loss_out;
+  a.normpart = h->normpart;
+  a.error = h->dp_error;
+  a.timeout_cycles = 4000000000LL;       // ~2 s at 1.9 GHz: a missing peer fails instead of hanging the GPU
+  dp_allreduce_kernel<<<h->n_norm, RED_IDX, 0, (cudaStream_t)stream>>>(a);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// the device int32 optax count (the `step` of mafb200_clip_adam) doubles as the exchange epoch
+int mafb200_dp_bind_step(mafb200_handle h, const int32_t* step) {
+  if (!h || !step) return fail("null argument");
+  h->dp_step = step;
+  return 0;
+}
+
+// forget all epochs (call on every rank, between host barriers, whenever the step counter restarts)
+int mafb200_dp_reset(mafb200_handle h) {
+  if (!h || !h->dp_sym) return fail("dp not initialised");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemset(h->dp_flags, 0, DP_MAX_WORLD * sizeof(unsigned int)));
+  CU(cudaMemset(h->dp_error, 0, 4));
+  CU(cudaDeviceSynchronize());
+  return 0;
+}
+
+int mafb200_dp_error(mafb200_handle h, int32_t* out) {
+  if (!h || !out) return fail("null argument");
+  *out = 0;
+  if (h->dp_error) {
+    unsigned int e = 0;
+    CU(cudaMemcpy(&e, h->dp_error, 4, cudaMemcpyDeviceToHost));
+    *out = (int32_t)e;
+  }
+  return 0;
 }
 
 int mafb200_set_wide_core(mafb200_handle h, int32_t core) {
@@ -995,10 +1105,16 @@ int mafb200_log_prob(mafb200_handle h, const float* params, const float* x, cons
 int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, const float* y, int64_t B,
                       float inv_global_B, const int32_t* batch_index, int64_t n_batches, float* out_loss,
                       float* out_grad, int32_t flags, void* stream) {
-  if (!h || !params || !x || !out_loss || !out_grad || (h->desc.n_cond && !y)) return fail("null argument");
+  if (!h || !params || !x || (h->desc.n_cond && !y)) return fail("null argument");
+  if (!(flags & MAFB200_DP_SLOT) && (!out_loss || !out_grad)) return fail("null argument");
   if (B <= 0) return fail("loss_grad needs a non-empty batch");
   if (batch_index && n_batches <= 0) return fail("n_batches must be positive");
   cudaStream_t st = (cudaStream_t)stream;
+  const bool dp_slot = (flags & MAFB200_DP_SLOT) != 0;
+  if (dp_slot) {
+    if (!h->dp_sym || !h->dp_step) return fail("MAFB200_DP_SLOT needs mafb200_dp_init and mafb200_dp_bind_step");
+    if (h->wide) return fail("the peer-memory all-reduce serves the fused narrow path; use NCCL for wide models");
+  }
   if (h->wide) {
     if (batch_index) return fail("device-side batch selection is not available on the wide path");
     if (wide_loss_grad(h, params, x, y, B, inv_global_B, out_loss, out_grad, flags, st)) return 1;
@@ -1029,8 +1145,11 @@ int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, con
   launch_flow<true>(P, A, grid, st);
   CU(cudaGetLastError());
   if (h->timing) CU(cudaEventRecord(h->ev1, st));
+  const size_t sf = dp_slot_floats(P);
   reduce_kernel<<<h->n_norm, RED_IDX * RED_PARTS, 0, st>>>(h->partial, grid, P.P, h->mask, out_grad,
-                                                         h->partial_loss, out_loss, h->normpart);
+                                                         h->partial_loss, out_loss, h->normpart,
+                                                         dp_slot ? h->dp_step : nullptr, h->dp_sym,
+                                                         h->dp_sym ? h->dp_sym + sf : nullptr);
   CU(cudaGetLastError());
   return 0;
 }

@@ -65,7 +65,14 @@ __global__ void pack_kernel(const __grid_constant__ Plan P, const float* __restr
 __global__ void __launch_bounds__(RED_IDX * RED_PARTS)
 reduce_kernel(const float* __restrict__ partial, int G, int P, const unsigned char* __restrict__ mask,
               float* __restrict__ grad, const float* __restrict__ partial_loss, float* __restrict__ loss,
-              float* __restrict__ normpart) {
+              float* __restrict__ normpart, const int* __restrict__ dp_step, float* dp_slot0,
+              float* dp_slot1) {
+  if (dp_step) {
+    // data parallel over peer memory: the reduced gradient goes to this rank's symmetric slot of the
+    // coming epoch (= optax count + 1, a device counter, so the step stays CUDA-graph capturable)
+    grad = ((dp_step[0] + 1) & 1) ? dp_slot1 : dp_slot0;
+    loss = grad + ((P + 3) & ~3);
+  }
   __shared__ float red[RED_PARTS][RED_IDX];
   __shared__ float wsum[RED_IDX / 32];
   const int i = threadIdx.x % RED_IDX, p = threadIdx.x / RED_IDX;

@@ -159,8 +159,39 @@ class MafEngine:
                 self._chk(ld, "ld"), _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
         return x, ld
 
+    # ---- data parallel over NVLink peer memory
+    def dp_init(self, rank, world):
+        """Allocate this rank's symmetric gradient buffer; returns its 64-byte CUDA IPC handle."""
+        buf = C.create_string_buffer(64)
+        _lib.check(self.lib.mafb200_dp_init(self._h, int(rank), int(world), buf))
+        return buf.raw
+
+    def dp_connect(self, handles):
+        """``handles``: the ranks' IPC handles, rank-major (list of 64-byte strings)."""
+        blob = b"".join(handles)
+        _lib.check(self.lib.mafb200_dp_connect(self._h, C.c_char_p(blob)))
+
+    def dp_bind_step(self, step):
+        """``step``: the int32 CUDA tensor that clip_adam increments (kept alive by the caller)."""
+        _lib.check(self.lib.mafb200_dp_bind_step(self._h, C.c_void_p(step.data_ptr())))
+        self._dp_step = step
+
+    def dp_reset(self):
+        _lib.check(self.lib.mafb200_dp_reset(self._h))
+
+    def dp_allreduce(self, out_grad, out_loss):
+        """One-shot peer all-reduce of the slots written by ``loss_grad(dp_slot=True)``; leaves the
+        norm partials current (``clip_adam(norm_current=True)``)."""
+        _lib.check(self.lib.mafb200_dp_allreduce(self._h, self._chk(out_grad, "out_grad"),
+                                                 self._chk(out_loss, "out_loss"), self._stream()))
+
+    def dp_error(self):
+        e = C.c_int32()
+        _lib.check(self.lib.mafb200_dp_error(self._h, C.byref(e)))
+        return e.value
+
     def loss_grad(self, params, x, y, out_loss, out_grad, batch_rows=None, inv_global_b=None,
-                  batch_index=None, n_batches=1, packed_current=False):
+                  batch_index=None, n_batches=1, packed_current=False, dp_slot=False):
         """out_loss[0], out_grad <- NLL and its gradient over rows [0, batch_rows) of x/y (or the
         device-selected batch ``batch_index[0] % n_batches``)."""
         px = self._chk(x, "x", self.n_in)
@@ -175,8 +206,8 @@ class MafEngine:
         inv = 1.0 / B if inv_global_b is None else float(inv_global_b)
         _lib.check(self.lib.mafb200_loss_grad(
             self._h, self._chk(params, "params"), px, py, B, inv, bi, int(n_batches),
-            self._chk(out_loss, "out_loss"), self._chk(out_grad, "out_grad"),
-            _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
+            None if dp_slot else self._chk(out_loss, "out_loss"), None if dp_slot else self._chk(out_grad, "out_grad"),
+            (_lib.PACKED_CURRENT if packed_current else 0) | (_lib.DP_SLOT if dp_slot else 0), self._stream()))
 
     @staticmethod
     def make_opt_desc(lr=1e-3, warmup=0.0, decay_steps=1e9, clip=5.0, b1=0.9, b2=0.999, eps=1e-8,

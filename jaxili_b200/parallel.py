@@ -54,3 +54,32 @@ def philox_row_offset(rank_start_row):
     """Sampling shards by rows: Philox subsequence = global row index, so samples do not depend on
     the number of GPUs."""
     return int(rank_start_row)
+
+
+# gradients up to this size use the one-shot peer-memory all-reduce (latency-bound regime);
+# larger ones (the wide config's 15 MB) stay on NCCL, whose ring/NVLS algorithms are bandwidth-optimal
+PEER_ALLREDUCE_MAX_BYTES = 1 << 20
+
+
+def setup_peer_allreduce(engine, step):
+    """Map every rank's symmetric gradient buffer into every other rank (CUDA IPC over NVLink) and
+    bind the device step counter ``step`` as the exchange epoch.  Returns True when the fused peer
+    all-reduce is available for this engine.  Collective: every rank must call it."""
+    rank, world = world_info()
+    if world == 1 or world > 8 or engine.n_params * 4 > PEER_ALLREDUCE_MAX_BYTES:
+        return False
+    if not getattr(engine, "_dp_ready", False):
+        handle = engine.dp_init(rank, world)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        engine.dp_connect(handles)
+        engine._dp_ready = True
+        engine._dp_step = None
+    if engine._dp_step is None or engine._dp_step.data_ptr() != step.data_ptr():
+        # a new step counter (new optimizer): epochs restart, forget the old ones on every rank
+        torch.cuda.synchronize()
+        dist.barrier()
+        engine.dp_reset()
+        engine.dp_bind_step(step)
+        dist.barrier()
+    return True

@@ -288,6 +288,16 @@ class TrainerModule:
             P = flat.numel()
             grad, loss = self._gbuf[:P], self._gbuf[-4:-3]
             _, world = parallel.world_info()
+            if world > 1 and parallel.setup_peer_allreduce(eng, state.step):
+                # latency-bound gradient (<= 1 MB): one-shot all-reduce over NVLink peer memory, fused
+                # with the norm partials; replicas stay bit-identical (fixed rank order)
+                eng.loss_grad(flat, x, y, loss, grad, inv_global_b=parallel.inv_global_batch(x.shape[0]),
+                              packed_current=self._packed, dp_slot=True)
+                eng.dp_allreduce(grad, loss)
+                eng.clip_adam(flat, grad, state.opt_state["m"], state.opt_state["v"], state.step, state.tx,
+                              norm_current=True)
+                self._packed = True
+                return state, {"loss": loss[0].clone()}
             parallel.dp_step(
                 lambda g: eng.loss_grad(flat, x, y, loss, grad, inv_global_b=parallel.inv_global_batch(x.shape[0]),
                                         packed_current=self._packed),
@@ -312,12 +322,14 @@ class TrainerModule:
         """CUDA-graph replay of one whole step over a GPU-resident dataset: the batch is selected on
         the device from the optax step counter, so one graph launch = forward + backward + reduction
         + clip + Adam with no host work.  Returns ``step() -> None`` (loss in ``self.last_loss``)."""
-        if parallel.world_info()[1] > 1:
-            # capturing the NCCL all-reduce together with the kernels hung on 2xB200 (torch 2.11 /
-            # NCCL 2.28.9); multi-rank steps are launched eagerly (TrainerModule.train_step)
-            raise NotImplementedError("make_graph_step is single-process; use train_step under torch.distributed")
         state = self.state
         eng = self.model.engine()
+        _, world = parallel.world_info()
+        peer = world > 1 and parallel.setup_peer_allreduce(eng, state.step)
+        if world > 1 and not peer:
+            # capturing the NCCL all-reduce together with the kernels hung on 2xB200 (torch 2.11 /
+            # NCCL 2.28.9); without the peer-memory path multi-rank steps are launched eagerly
+            raise NotImplementedError("make_graph_step under torch.distributed needs the peer-memory all-reduce")
         xd, yd = self._batch_xy([theta_dev, x_dev])
         n_batches = xd.shape[0] // batch_size
         flat = state.params.flat
@@ -326,9 +338,13 @@ class TrainerModule:
         self.last_loss = loss
         eng.pack(flat)
 
+        inv = 1.0 / (batch_size * world)
+
         def body():
-            eng.loss_grad(flat, xd, yd, loss, grad, batch_rows=batch_size, batch_index=state.step,
-                          n_batches=n_batches, packed_current=True)
+            eng.loss_grad(flat, xd, yd, loss, grad, batch_rows=batch_size, inv_global_b=inv,
+                          batch_index=state.step, n_batches=n_batches, packed_current=True, dp_slot=peer)
+            if peer:
+                eng.dp_allreduce(grad, loss)       # own kernel over NVLink peer memory: graph-capturable
             eng.clip_adam(flat, grad, state.opt_state["m"], state.opt_state["v"], state.step, state.tx,
                           norm_current=True)
 
