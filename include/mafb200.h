@@ -13,6 +13,8 @@
  *                                 jaxili/train.py:337-340 eval_step)
  *   mafb200_loss_grad         <- jax.value_and_grad(loss_nll_npe / loss_nll_nle)
  *                                jaxili/train.py:330-332, jaxili/loss.py:35-83
+ *   mafb200_log_prob_grad_y   <- jax.grad of MCMCPosterior.log_likelihood w.r.t. theta (NLE)
+ *                                jaxili/posterior/mcmc_posterior.py:139-159, 194-201
  *   mafb200_clip_adam         <- state.apply_gradients(grads) with the optax chain built in
  *                                jaxili/train.py:246-300 (clip_by_global_norm -> adam(warmup_cosine))
  *   mafb200_forward           <- ConditionalMAF.__call__ (u, log_det)  jaxili/model.py:848-874
@@ -183,6 +185,12 @@ int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, con
                       int64_t B, float inv_global_B,
                       const int32_t* batch_index, int64_t n_batches,
                       float* out_loss, float* out_grad, int32_t flags, void* stream);
+
+/* out_logp[b] (nullable) = log p(x_b | y_b), out_dy[b][c] = d log p(x_b | y_b) / d y_b[c]: gradient with
+   respect to the conditioning input -- what NUTS/HMC over an NLE likelihood differentiates
+   (jaxili/posterior/mcmc_posterior.py:139-159, 194-201).  Fused (narrow) path only. */
+int mafb200_log_prob_grad_y(mafb200_handle h, const float* params, const float* x, const float* y,
+                            int64_t B, float* out_logp, float* out_dy, int32_t flags, void* stream);
 
 /* optax.chain(clip_by_global_norm, adam(schedule)) + apply_gradients, in place on
    params / m / v; step[0] (device int32) is the optax count and is incremented.

@@ -75,6 +75,8 @@ SYMBOLS = {
     "mafb200_loss_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_float, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                     C.c_int32, C.c_void_p]),
+    "mafb200_log_prob_grad_y": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mafb200_clip_adam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.POINTER(MafOptDesc), C.c_int32, C.c_void_p]),
     "mafb200_sample_from_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

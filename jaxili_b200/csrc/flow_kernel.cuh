@@ -28,6 +28,9 @@ struct FlowArgs {
   float* out_logp;            // forward-only: [B] (nullable)
   float* out_u;               // forward-only: [B][D] base-space point u (nullable)
   float* out_logdet;          // forward-only: [B] summed log|det J| of the MAF (nullable)
+  float* out_dy;              // reverse pass: [B][C] gradient w.r.t. the RAW conditioner rows (nullable);
+                              // with it the input-gradient product of the first linear covers the
+                              // conditioner columns and no weight gradients are scheduled
   float* partial_grad;        // training: [grid][P]
   float* partial_loss;        // training: [grid]
   int Rt;                     // rows per tile in this launch (multiple of 4, <= Plan::R)
@@ -287,6 +290,8 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
         }
       }
     }
+    if (BWD && A.out_dy)
+      for (int idx = tid; idx < (P.lin[0].KP - P.DP + 4) * RP; idx += NT) sm[P.o_gy + idx] = 0.f;
     __syncthreads();
     stamp(2);
     if (ti + 1 < my_n) stage_issue(ti + 1);
@@ -314,6 +319,7 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
       if (BWD) {
         const float contrib = warp_sum(r < valid ? -lp * A.inv_b : 0.f);
         if (lane == 0) atomicAdd(loss_acc, contrib);
+        if (A.out_logp && r < valid) A.out_logp[row0 + r] = lp;
       } else if (r < valid) {
         if (A.out_logp) A.out_logp[row0 + r] = lp;
         if (A.out_logdet) A.out_logdet[row0 + r] = ldsum;
@@ -395,11 +401,17 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
                     for (int q = 0; q < TS; ++q)
                       gv[q] = RELU ? (dv[q] > 0.f ? res[cc][q] : 0.f) : res[cc][q] * dv[q];
                     stv(sm + P.o_g[(i - 1) & 1] + c * RP + o_r0, gv);
-                  } else {       // gradient w.r.t. this layer's input x: MADE path + direct path
+                  } else if (c < D || !A.out_dy) {   // gradient w.r.t. this layer's input x: MADE + direct path
                     ldv(dv, gx + c * RP + o_r0);
 #pragma unroll
                     for (int q = 0; q < TS; ++q) gv[q] = res[cc][q] + dv[q];
                     stv(gu + c * RP + o_r0, gv);
+                  } else if (c < P.K0) {             // dy mode, conditioner columns: summed over the layers
+                    float* gyp = sm + P.o_gy + (c - D) * RP + o_r0;
+                    ldv(dv, gyp);
+#pragma unroll
+                    for (int q = 0; q < TS; ++q) gv[q] = res[cc][q] + dv[q];
+                    stv(gyp, gv);
                   }
                 }
               }
@@ -417,6 +429,14 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
           __syncthreads();
           stamp(20 + i);
         }
+      }
+      if (A.out_dy) {   // d/dy = (d/dy') / std (Standardizer), rows are contiguous in HBM: coalesced store
+        float* dst = A.out_dy + row0 * C;
+        for (int idx = tid; idx < valid * C; idx += NT) {
+          const int r = idx / C, c = idx - r * C;
+          dst[idx] = __fdiv_rn(sm[P.o_gy + c * RP + r], cst[2 * D + C + c]);
+        }
+        __syncthreads();
       }
     }
   }

@@ -177,6 +177,8 @@ bool plan_layout(Plan& P, int R, bool stash_all, int n_wbuf, int limit) {
   o += P.DP * RP;
   P.o_cst = o;
   o += r4(2 * P.D + 2 * P.C);
+  P.o_gy = o;
+  o += (r4(P.K0) - P.DP + 4) * RP;        // conditioner rows of the padded MADE input (dy mode)
   P.o_g[0] = o;
   o += maxhp * RP;
   P.o_g[1] = o;
@@ -1038,7 +1040,7 @@ static int flow_timing_begin(mafb200_handle h, cudaStream_t st) {
 }
 
 // work-list geometry of one launch (see FlowArgs::Phase)
-static void fill_phases(const Plan& P, FlowArgs& A) {
+static void fill_phases(const Plan& P, FlowArgs& A, bool want_dy = false, bool skip_wgrad = false) {
   const int nRB = A.Rt / 4;
   int s = 0;
   while ((1 << s) < nRB) ++s;          // nRB <= 8 -> s <= 3
@@ -1048,7 +1050,7 @@ static void fill_phases(const Plan& P, FlowArgs& A) {
     const LinDesc& ln = P.lin[i];
     FlowArgs::Phase& ph = A.ph[i];
     ph.fB = (ln.NP / 4 + cpw - 1) / cpw;
-    ph.xC = (i == 0 ? P.DP : ln.KP) / 4;
+    ph.xC = (i == 0 ? (want_dy ? ln.KP : P.DP) : ln.KP) / 4;   // dy mode: also the conditioner columns
     ph.xB = (ph.xC + cpw - 1) / cpw;
     ph.nKB = (ln.K + 1 + 3) / 4;
     ph.nNB = (ln.N + 3) / 4;
@@ -1058,7 +1060,7 @@ static void fill_phases(const Plan& P, FlowArgs& A) {
     ph.nbg = (ph.nNB + (1 << nbs) - 1) >> nbs;
     const int kpw = 16 >> nbs;
     ph.nKG = (ph.nKB + kpw - 1) / kpw;
-    ph.bB = ph.nKG * ph.nbg;
+    ph.bB = skip_wgrad ? 0 : ph.nKG * ph.nbg;
   }
 }
 
@@ -1150,6 +1152,42 @@ int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, con
                                                          h->partial_loss, out_loss, h->normpart,
                                                          dp_slot ? h->dp_step : nullptr, h->dp_sym,
                                                          h->dp_sym ? h->dp_sym + sf : nullptr);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// out_logp[b] = log p(x_b | y_b) and out_dy[b][c] = d log p(x_b | y_b) / d y_b[c]: the gradient with
+// respect to the CONDITIONING input, i.e. what HMC/NUTS over an NLE likelihood differentiates
+// (jaxili/posterior/mcmc_posterior.py:139-159, 194-201).  Same fused kernel as loss_grad run with
+// 1/B := -1 (so the "loss" is sum_b log p_b, whose y-gradient is per row), with the weight-gradient
+// work list switched off and the input-gradient product extended to the conditioner columns.
+int mafb200_log_prob_grad_y(mafb200_handle h, const float* params, const float* x, const float* y, int64_t B,
+                            float* out_logp, float* out_dy, int32_t flags, void* stream) {
+  if (!h || !params || !x || !y || !out_dy) return fail("null argument");
+  if (h->desc.n_cond == 0) return fail("the model has no conditioning input");
+  if (h->wide) return fail("log_prob_grad_y is implemented on the fused (narrow) path only");
+  if (B <= 0) return B == 0 ? 0 : fail("negative batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!(flags & MAFB200_PACKED_CURRENT) && mafb200_pack(h, params, stream)) return 1;
+  FlowArgs A{};
+  A.wimg = h->wimg;
+  A.x = x;
+  A.y = y;
+  A.B = B;
+  A.n_batches = 1;
+  A.stdc = h->stdc;
+  A.logdet_const = h->logdet_const;
+  A.inv_b = -1.f;
+  A.out_logp = out_logp;
+  A.out_dy = out_dy;
+  A.partial_grad = h->partial;        // unused: no weight-gradient tasks are scheduled
+  A.partial_loss = h->partial_loss;
+  A.trace = nullptr;
+  int grid;
+  const Plan* pp;
+  if (launch_geometry(h, B, pp, A.Rt, A.n_tiles, grid)) return 1;
+  fill_phases(*pp, A, /*want_dy=*/true, /*skip_wgrad=*/true);
+  launch_flow<true>(*pp, A, grid, st);
   CU(cudaGetLastError());
   return 0;
 }

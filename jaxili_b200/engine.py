@@ -159,6 +159,21 @@ class MafEngine:
                 self._chk(ld, "ld"), _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
         return x, ld
 
+    def log_prob_grad_y(self, params, x, y, packed_current=False):
+        """(log_prob [B], d log_prob / d y [B, n_cond]): gradient w.r.t. the conditioning input."""
+        px = self._chk(x, "x", self.n_in)
+        py = self._chk(y, "y", self.n_cond)
+        B = x.shape[0]
+        if y.shape[0] != B:
+            raise ValueError("x and y must have the same number of rows")
+        lp = torch.empty(B, dtype=torch.float32, device=self.device)
+        dy = torch.empty((B, self.n_cond), dtype=torch.float32, device=self.device)
+        if B:
+            _lib.check(self.lib.mafb200_log_prob_grad_y(
+                self._h, self._chk(params, "params"), px, py, B, self._chk(lp, "lp"), self._chk(dy, "dy"),
+                _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
+        return lp, dy
+
     # ---- data parallel over NVLink peer memory
     def dp_init(self, rank, world):
         """Allocate this rank's symmetric gradient buffer; returns its 64-byte CUDA IPC handle."""

@@ -367,6 +367,14 @@ class NDE_w_Standardization(NDENetwork):
     def log_prob(self, x, y=None, model="NPE"):
         return self.__call__(x, y, model)
 
+    def log_prob_and_grad_cond(self, x, y):
+        """(log_prob, d log_prob / d y) -- the value and gradient an HMC/NUTS sampler over an NLE
+        likelihood needs (jax.grad of jaxili/posterior/mcmc_posterior.py:139-159 w.r.t. theta)."""
+        eng = self.engine()
+        x = as_device_f32(x, eng.device, self.nde.n_in)
+        y = self._fused._cond(y, x.shape[0], eng)
+        return eng.log_prob_grad_y(self.flat_params(), x, y)
+
     def sample(self, y, num_samples, key, model="NPE"):
         assert model in ["NPE", "NLE"], "Model should be either 'NPE' or 'NLE'."
         eng = self.engine()

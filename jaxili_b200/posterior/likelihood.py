@@ -24,6 +24,16 @@ class LikelihoodEvaluator(NeuralPosterior):
             x = x.expand(theta.shape[0], -1) if isinstance(x, torch.Tensor) else np.repeat(x, theta.shape[0], axis=0)
         return self.model.apply({"params": self.state.params}, x, theta, method="log_prob")
 
+    def log_likelihood_and_grad(self, x, theta):
+        """(log p(x | theta), d log p(x | theta) / d theta) for a batch of theta (many chains at once):
+        the potential-energy gradient NUTS/HMC evaluates per leapfrog step
+        (jaxili/posterior/mcmc_posterior.py:194-201), from one fused forward+reverse kernel launch."""
+        x = x.reshape(1, -1) if len(x.shape) == 1 else x
+        theta = theta.reshape(1, -1) if len(theta.shape) == 1 else theta
+        if x.shape[0] == 1 and theta.shape[0] > 1:
+            x = x.expand(theta.shape[0], -1) if isinstance(x, torch.Tensor) else np.repeat(x, theta.shape[0], axis=0)
+        return self.model.apply({"params": self.state.params}, x, theta, method="log_prob_and_grad_cond")
+
     def unnormalized_log_prob(self, theta, x=None):
         x = self.x if x is None else x
         if x is None:
