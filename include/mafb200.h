@@ -15,6 +15,8 @@
  *                                jaxili/train.py:330-332, jaxili/loss.py:35-83
  *   mafb200_log_prob_grad_y   <- jax.grad of MCMCPosterior.log_likelihood w.r.t. theta (NLE)
  *                                jaxili/posterior/mcmc_posterior.py:139-159, 194-201
+ *   mafb200_hmc_trajectory    <- numpyro HMC leapfrog integration inside MCMCPosterior.sample
+ *                                jaxili/posterior/mcmc_posterior.py:78-118, 248-305
  *   mafb200_clip_adam         <- state.apply_gradients(grads) with the optax chain built in
  *                                jaxili/train.py:246-300 (clip_by_global_norm -> adam(warmup_cosine))
  *   mafb200_forward           <- ConditionalMAF.__call__ (u, log_det)  jaxili/model.py:848-874
@@ -101,6 +103,25 @@ typedef struct {
   float weight_decay;  /* adamw only */
   int32_t kind;        /* 0 adam, 1 sgd (+decayed weights), 2 adamw */
 } MafOptDesc;
+
+/* State of n vectorised HMC chains over  theta -> log_prior(theta) + log p(x | theta)  in the unconstrained
+   space z of the prior's support (what numpyro's HMC/NUTS do inside MCMCPosterior,
+   jaxili/posterior/mcmc_posterior.py:179-305).  All pointers are DEVICE pointers owned by the caller.
+   prior_kind[c]: 0 = Normal(loc = lo[c], scale = hi[c]) on the real line (theta = z),
+                  1 = Uniform(lo[c], hi[c]) (theta = lo + (hi - lo) sigmoid(z)). */
+typedef struct {
+  const float* eps;            /* [1]  leapfrog step size (device scalar, so adaptation needs no re-capture) */
+  const float* inv_mass;       /* [C]  diagonal inverse mass matrix */
+  const int32_t* prior_kind;   /* [C] */
+  const float* lo;             /* [C] */
+  const float* hi;             /* [C] */
+  float* z;                    /* [n][C] in/out  position */
+  float* p;                    /* [n][C] in/out  momentum */
+  float* g;                    /* [n][C] in/out  gradient of the log density at z */
+  float* logdens;              /* [n]    out     log density at z (up to a constant) */
+  float* theta;                /* [n][C] out     constrained position */
+  float* scratch;              /* [n][C + 1]     work space */
+} MafHmcState;
 
 const char* mafb200_last_error(void);
 int mafb200_version(void);
@@ -191,6 +212,14 @@ int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, con
    (jaxili/posterior/mcmc_posterior.py:139-159, 194-201).  Fused (narrow) path only. */
 int mafb200_log_prob_grad_y(mafb200_handle h, const float* params, const float* x, const float* y,
                             int64_t B, float* out_logp, float* out_dy, int32_t flags, void* stream);
+
+/* n_steps leapfrog steps of all n chains for the observation rows x [n][n_in] (the observation repeated per
+   chain): 3 launches per step (drift -> fused flow forward+reverse -> kick), enqueued without synchronising.
+   n_steps = 0 evaluates theta, g and logdens at the current z without moving (initialisation).
+   Replaces the potential-energy/gradient evaluations of numpyro inside MCMCPosterior._hmc_numpyro /
+   _nuts_numpyro, jaxili/posterior/mcmc_posterior.py:194-305. */
+int mafb200_hmc_trajectory(mafb200_handle h, const float* params, const float* x, int64_t n,
+                           const MafHmcState* state, int32_t n_steps, int32_t flags, void* stream);
 
 /* optax.chain(clip_by_global_norm, adam(schedule)) + apply_gradients, in place on
    params / m / v; step[0] (device int32) is the optax count and is incremented.

@@ -42,6 +42,11 @@ class MafOptDesc(C.Structure):
     ]
 
 
+class MafHmcState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("eps", "inv_mass", "prior_kind", "lo", "hi", "z", "p", "g", "logdens", "theta", "scratch")]
+
+
 # name -> (restype, argtypes); every symbol include/mafb200.h declares
 SYMBOLS = {
     "mafb200_last_error": (C.c_char_p, []),
@@ -77,6 +82,8 @@ SYMBOLS = {
                                     C.c_int32, C.c_void_p]),
     "mafb200_log_prob_grad_y": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                           C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mafb200_hmc_trajectory": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(MafHmcState),
+                                         C.c_int32, C.c_int32, C.c_void_p]),
     "mafb200_clip_adam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.POINTER(MafOptDesc), C.c_int32, C.c_void_p]),
     "mafb200_sample_from_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -14,6 +14,7 @@
 #include "opt_kernels.cuh"
 #include "sample_kernel.cuh"
 #include "dp_kernel.cuh"
+#include "hmc_kernels.cuh"
 #include "wide_kernels.cuh"
 #include "wide_tc.cuh"
 
@@ -1189,6 +1190,49 @@ int mafb200_log_prob_grad_y(mafb200_handle h, const float* params, const float* 
   fill_phases(*pp, A, /*want_dy=*/true, /*skip_wgrad=*/true);
   launch_flow<true>(*pp, A, grid, st);
   CU(cudaGetLastError());
+  return 0;
+}
+
+int mafb200_hmc_trajectory(mafb200_handle h, const float* params, const float* x, int64_t n,
+                           const MafHmcState* s, int32_t n_steps, int32_t flags, void* stream) {
+  if (!h || !params || !x || !s) return fail("null argument");
+  if (!s->eps || !s->inv_mass || !s->prior_kind || !s->lo || !s->hi || !s->z || !s->p || !s->g || !s->logdens ||
+      !s->theta || !s->scratch)
+    return fail("null pointer in MafHmcState");
+  if (n <= 0 || n_steps < 0) return fail("hmc_trajectory needs n > 0 and n_steps >= 0");
+  if (h->desc.n_cond == 0) return fail("the model has no conditioning input");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!(flags & MAFB200_PACKED_CURRENT) && mafb200_pack(h, params, stream)) return 1;
+  const int C = h->desc.n_cond;
+  HmcArgs A{};
+  A.eps = s->eps;
+  A.inv_mass = s->inv_mass;
+  A.kind = s->prior_kind;
+  A.lo = s->lo;
+  A.hi = s->hi;
+  A.z = s->z;
+  A.p = s->p;
+  A.g = s->g;
+  A.theta = s->theta;
+  A.dll = s->scratch;
+  A.ll = s->scratch + n * C;
+  A.logdens = s->logdens;
+  A.n = n;
+  A.C = C;
+  const int bd = (int)std::min<int64_t>((n * C + 255) / 256, 4 * (int64_t)h->n_sm);
+  const int bk = (int)std::min<int64_t>((n + 7) / 8, 4 * (int64_t)h->n_sm);
+  const int steps = n_steps > 0 ? n_steps : 1;
+  for (int i = 0; i < steps; ++i) {
+    A.kick = n_steps > 0 ? 0.5f : 0.f;
+    A.drift = n_steps > 0 ? 1.f : 0.f;
+    hmc_drift_kernel<<<bd, 256, 0, st>>>(A);
+    CU(cudaGetLastError());
+    if (mafb200_log_prob_grad_y(h, params, x, s->theta, n, s->scratch + n * C, s->scratch,
+                                MAFB200_PACKED_CURRENT, stream))
+      return 1;
+    hmc_kick_kernel<<<bk, 256, 0, st>>>(A);
+    CU(cudaGetLastError());
+  }
   return 0;
 }
 

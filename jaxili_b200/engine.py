@@ -174,6 +174,29 @@ class MafEngine:
                 _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
         return lp, dy
 
+    def hmc_trajectory(self, params, x_rep, state, n_steps, packed_current=False):
+        """``n_steps`` leapfrog steps of all chains (``n_steps=0``: evaluate gradient and log density only).
+        ``state``: dict of CUDA tensors eps[1], inv_mass[C], prior_kind[C] (int32), lo[C], hi[C], z[n,C],
+        p[n,C], g[n,C], logdens[n], theta[n,C], scratch[n*(C+1)] -- updated in place."""
+        n = state["z"].shape[0]
+        px = self._chk(x_rep, "x", self.n_in)
+        if x_rep.shape[0] != n:
+            raise ValueError("x must hold one observation row per chain")
+        st = _lib.MafHmcState()
+        for name, shape, dt in (("eps", (1,), torch.float32), ("inv_mass", (self.n_cond,), torch.float32),
+                                ("prior_kind", (self.n_cond,), torch.int32), ("lo", (self.n_cond,), torch.float32),
+                                ("hi", (self.n_cond,), torch.float32), ("z", (n, self.n_cond), torch.float32),
+                                ("p", (n, self.n_cond), torch.float32), ("g", (n, self.n_cond), torch.float32),
+                                ("logdens", (n,), torch.float32), ("theta", (n, self.n_cond), torch.float32),
+                                ("scratch", (n * (self.n_cond + 1),), torch.float32)):
+            t = state[name]
+            if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != self.device:
+                raise ValueError(f"hmc state '{name}' must be a contiguous {dt} tensor of shape {shape} on {self.device}")
+            setattr(st, name, t.data_ptr())
+        _lib.check(self.lib.mafb200_hmc_trajectory(
+            self._h, self._chk(params, "params"), px, n, C.byref(st), int(n_steps),
+            _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
+
     # ---- data parallel over NVLink peer memory
     def dp_init(self, rank, world):
         """Allocate this rank's symmetric gradient buffer; returns its 64-byte CUDA IPC handle."""

@@ -45,12 +45,12 @@ class NLE(NPE):
 
     def build_posterior(self, prior_distr=None, verbose: Optional[bool] = None, x=None,
                         mcmc_method: Optional[str] = "nuts_numpyro", mcmc_kwargs: Optional[Dict[str, Any]] = None):
-        """jaxili/inference/nle.py:522-574 builds an MCMCPosterior on numpyro NUTS.  numpyro is a
-        third-party sampler outside this hot path (MCMC is out of scope; its inner
-        call, ``log_prob``, is the fused kernel).  The likelihood object returned here exposes that
-        call so an external sampler can drive it."""
+        """jaxili/inference/nle.py:522-574: wrap the trained likelihood in an ``MCMCPosterior``.  The sampler
+        is the vectorised-chains HMC of ``jaxili_b200.posterior.mcmc_posterior`` (numpyro is not on this
+        path); ``prior_distr`` is a ``jaxili_b200.priors`` distribution (``Uniform`` / ``Normal``), needed
+        only once ``sample`` is called."""
         self._require("trainer", "No trainer found. You must first create a trainer.")
-        from ..posterior.likelihood import LikelihoodEvaluator
-        return LikelihoodEvaluator(model=self.trainer.model, state=self.trainer.state,
-                                   verbose=self.verbose if verbose is None else verbose, x=x,
-                                   prior_distr=prior_distr)
+        from ..posterior.mcmc_posterior import MCMCPosterior
+        return MCMCPosterior(model=self.trainer.model, state=self.trainer.state, prior_distr=prior_distr,
+                             verbose=self.verbose if verbose is None else verbose, x=x,
+                             mcmc_method=mcmc_method, mcmc_kwargs=mcmc_kwargs)

@@ -2,3 +2,4 @@
 
 from .base_posterior import NeuralPosterior
 from .direct_posterior import DirectPosterior
+from .mcmc_posterior import MCMCPosterior

@@ -228,8 +228,35 @@ def test_nle_end_to_end(tmp_path):
     # training lowers the NLL: true theta explains x[0] better than a far-away theta
     far = theta[:1].copy() + 2.5
     assert like.log_likelihood(x[0], theta[:1]).item() > like.log_likelihood(x[0], far).item()
+    with pytest.raises(ValueError):
+        like.sample(10)                     # no prior set
+    # MCMC over the learned likelihood (jaxili/tests/test_posterior.py:102-166): shapes, support, and
+    # agreement of the chains with a self-normalised importance-sampling estimate from the same density
+    from jaxili_b200.priors import Uniform
+    prior = Uniform(-3.0 * np.ones(5, np.float32), 3.0 * np.ones(5, np.float32))
+    post = inf.build_posterior(prior_distr=prior, x=x[0].reshape(1, -1))
+    assert post.mcmc_method == "nuts_numpyro" and post.mcmc_kwargs == {}
+    assert post.log_prior(torch.as_tensor(theta[:10])).shape == (10,)
+    assert post.unnormalized_log_prob(theta[:10], x[:10]).shape == (10,)
+    post.set_mcmc_kwargs({"num_warmup": 60})
+    s1 = post.sample(num_samples=100, key=0)
+    assert s1.shape == (100, 5) and torch.isfinite(s1).all()
+    post.set_mcmc_method("hmc_numpyro")
+    post.set_mcmc_kwargs({"num_chains": 512, "num_warmup": 200})
+    s = post.sample(num_samples=40, key=3)
+    assert s.shape == (512 * 40, 5) and torch.isfinite(s).all()
+    assert (s > -3).all() and (s < 3).all()
+    assert 0.5 < post.last_run["accept_prob"] < 0.99
+    cand = prior.sample(key=11, sample_shape=(1 << 20,))
+    w = torch.softmax(post.unnormalized_log_prob(cand).double(), dim=0)
+    is_mean = (w[:, None] * cand.double()).sum(0)
+    is_std = ((w[:, None] * (cand.double() - is_mean) ** 2).sum(0)).sqrt()
+    ess = 1.0 / float((w * w).sum())
+    assert ess > 500, ess
+    assert torch.allclose(s.double().mean(0), is_mean, atol=0.12), (s.mean(0), is_mean)
+    assert torch.allclose(s.double().std(0), is_std, rtol=0.15, atol=0.03), (s.std(0), is_std)
     with pytest.raises(NotImplementedError):
-        like.sample(10)
+        post.set_mcmc_method("wrong_method")
 
 
 def test_errors_like_reference():

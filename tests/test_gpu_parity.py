@@ -210,3 +210,52 @@ def test_log_prob_grad_wrt_conditioner(name, B, act):
     assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
     l_ref, g_ref = onp.nll_loss_and_grad(spec, flat.astype(np.float64), std, x.astype(np.float64), y.astype(np.float64))
     assert rel_err(out[1][0], l_ref) < TOL and grad_err(out[1][1], g_ref) < (1e-3 if act == "relu" else TOL)
+
+
+@pytest.mark.parametrize("name,act,n_steps", [("c3", "silu", 3), ("c1", "tanh", 5), ("c3", "silu", 0)])
+def test_hmc_trajectory_matches_restatement(name, act, n_steps):
+    """Leapfrog steps of many chains (drift -> fused flow d/dy -> kick) against oracle/hmc_numpy.py driven by
+    the float64 torch restatement of the flow's log-likelihood and its theta-gradient."""
+    from oracle import hmc_numpy
+    from oracle.maf_torch import TorchMaf
+    n = 193
+    spec, flat, std, x, y = make_case(CONFIGS[name], n, seed=5, activation=act)
+    eng = _engine(spec, std)
+    C = spec.n_cond
+    rng = np.random.default_rng(9)
+    kind = (np.arange(C) % 2).astype(np.int32)                 # alternate Normal / Uniform dimensions
+    lo = np.where(kind == 1, -2.0, 0.3).astype(np.float32)
+    hi = np.where(kind == 1, 2.5, 1.5).astype(np.float32)
+    z0 = rng.normal(size=(n, C)).astype(np.float32)
+    p0 = rng.normal(size=(n, C)).astype(np.float32)
+    inv_mass = rng.uniform(0.5, 2.0, size=C).astype(np.float32)
+    eps = 0.05
+    x_obs = np.repeat(x[:1], n, axis=0)
+    tm = TorchMaf(spec, std, torch.float64)
+    fl = torch.tensor(flat, dtype=torch.float64)
+    xt = torch.tensor(x_obs, dtype=torch.float64)
+
+    def loglik_and_grad(theta):
+        th = torch.tensor(theta, dtype=torch.float64, requires_grad=True)
+        ll = tm.log_prob(fl, xt, th)
+        ll.sum().backward()
+        return ll.detach().numpy(), th.grad.numpy()
+
+    k64, lo64, hi64 = kind.astype(np.int64), lo.astype(np.float64), hi.astype(np.float64)
+    ld0, g0, th0 = hmc_numpy.log_density_and_grad(z0.astype(np.float64), k64, lo64, hi64, loglik_and_grad)
+    S = {"eps": _t(np.array([eps], np.float32)), "inv_mass": _t(inv_mass),
+         "prior_kind": torch.as_tensor(kind, device="cuda:0"), "lo": _t(lo), "hi": _t(hi),
+         "z": _t(z0), "p": _t(p0), "g": torch.zeros(n, C, device="cuda:0"),
+         "logdens": torch.zeros(n, device="cuda:0"), "theta": torch.zeros(n, C, device="cuda:0"),
+         "scratch": torch.zeros(n * (C + 1), device="cuda:0")}
+    eng.hmc_trajectory(_t(flat), _t(x_obs), S, 0)
+    assert grad_err(S["g"].cpu().numpy(), g0) < TOL and rel_err(S["logdens"].cpu().numpy(), ld0) < TOL
+    assert np.array_equal(S["z"].cpu().numpy(), z0) and np.array_equal(S["p"].cpu().numpy(), p0)
+    if n_steps == 0:
+        return
+    z1, p1, g1, ld1, th1 = hmc_numpy.leapfrog(z0.astype(np.float64), p0.astype(np.float64), g0, eps,
+                                              inv_mass.astype(np.float64), n_steps, k64, lo64, hi64, loglik_and_grad)
+    eng.hmc_trajectory(_t(flat), _t(x_obs), S, n_steps, packed_current=True)
+    for key, ref in (("z", z1), ("p", p1), ("g", g1), ("theta", th1)):
+        assert grad_err(S[key].cpu().numpy(), ref) < 2e-5, key
+    assert rel_err(S["logdens"].cpu().numpy(), ld1) < 2e-5

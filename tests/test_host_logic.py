@@ -247,3 +247,63 @@ def test_data_parallel_world_size_2_gloo(tmp_path):
         params, _, _ = onp.clip_adam_step(params, g, st, 1e-2, 0.1, 100, clip=0.5)
     assert np.max(np.abs(a[:-1] - params)) < 1e-12
     assert abs(a[-1] - loss) < 1e-12 * abs(loss)
+
+
+def test_hmc_restatement_is_symplectic_and_reversible():
+    """oracle/hmc_numpy.py on an analytic Gaussian likelihood: energy error O(eps^2), exact reversibility."""
+    from oracle import hmc_numpy
+    rng = np.random.default_rng(0)
+    n, C = 16, 4
+    prec = np.array([1.0, 4.0, 0.25, 2.0])
+
+    def ll_grad(theta):
+        return -0.5 * (theta ** 2 * prec).sum(1), -theta * prec
+
+    kind = np.array([0, 1, 0, 1]); lo = np.array([0.0, -3.0, 0.5, -1.0]); hi = np.array([2.0, 3.0, 1.0, 4.0])
+    z = rng.normal(size=(n, C)); p = rng.normal(size=(n, C)); im = np.ones(C)
+    ld, g, _ = hmc_numpy.log_density_and_grad(z, kind, lo, hi, ll_grad)
+    # analytic gradient against central differences
+    h = 1e-6
+    for c in range(C):
+        dz = np.zeros(C); dz[c] = h
+        num = (hmc_numpy.log_density_and_grad(z + dz, kind, lo, hi, ll_grad)[0]
+               - hmc_numpy.log_density_and_grad(z - dz, kind, lo, hi, ll_grad)[0]) / (2 * h)
+        assert np.allclose(num, g[:, c], rtol=1e-5, atol=1e-6)
+    errs = []
+    for eps in (0.02, 0.01):
+        z1, p1, g1, ld1, _ = hmc_numpy.leapfrog(z, p, g, eps, im, int(0.4 / eps), kind, lo, hi, ll_grad)
+        errs.append(np.abs((-ld1 + 0.5 * (p1 ** 2).sum(1)) - (-ld + 0.5 * (p ** 2).sum(1))).max())
+    assert errs[1] < errs[0] / 3.0                       # second-order integrator
+    zb, pb, _, _, _ = hmc_numpy.leapfrog(z1, -p1, g1, 0.01, im, 40, kind, lo, hi, ll_grad)
+    assert np.allclose(zb, z, atol=1e-9) and np.allclose(-pb, p, atol=1e-9)
+
+
+def test_mcmc_host_pieces():
+    from jaxili_b200.posterior.mcmc_posterior import _DualAveraging, _warmup_windows, MCMCPosterior
+    from jaxili_b200.priors import Uniform, Normal
+    assert _warmup_windows(10) == (0, [])
+    init, ends = _warmup_windows(500)
+    assert init == 75 and ends == [100, 150, 250, 450]
+    init, ends = _warmup_windows(100)
+    assert init == 15 and ends == [90]
+    # dual averaging drives a monotone acceptance curve to the target
+    da, eps = _DualAveraging(1.0, 0.8), 1.0
+    for _ in range(400):
+        eps = da.update(float(np.exp(-eps)))             # accept(eps) = exp(-eps): target at eps = -ln 0.8
+    assert abs(da.final() + np.log(0.8)) < 0.02
+    u = Uniform(-np.ones(3, np.float32), 2 * np.ones(3, np.float32))
+    t = torch.tensor([[0.0, 0.5, 1.9], [0.0, 2.5, 0.0]])
+    lp = u.log_prob(t)
+    assert lp.shape == (2, 3) and torch.allclose(lp[0], torch.full((3,), -np.log(3.0))) and lp[1, 1] == -np.inf
+    assert u.sample(key=1, sample_shape=(7,), device="cpu").shape == (7, 3)
+    nrm = Normal(np.zeros(2, np.float32), 2.0)
+    assert torch.allclose(nrm.log_prob(torch.zeros(1, 2)), torch.full((1, 2), -np.log(2.0) - 0.5 * np.log(2 * np.pi)))
+    k, lo, hi = nrm.bounds()
+    assert k.tolist() == [0, 0] and hi.tolist() == [2.0, 2.0]
+    with pytest.raises(NotImplementedError):
+        MCMCPosterior(None, None, u, mcmc_method="wrong_method")
+    post = MCMCPosterior(None, None, u)
+    assert post.mcmc_method == "nuts_numpyro" and post.mcmc_kwargs == {}
+    assert post.log_prior(t).shape == (2,)
+    with pytest.raises(ValueError):
+        post.sample(10)
