@@ -100,6 +100,13 @@ class MafEngine:
         _lib.check(self.lib.mafb200_query(self._h, *[C.byref(a) for a in v]))
         return dict(smem_bytes=v[0].value, tile_rows=v[1].value, max_ctas=v[2].value, stash_all=v[3].value)
 
+    @property
+    def wide(self):
+        """True when the MADE does not fit shared memory and runs layer by layer (wide path)."""
+        if not hasattr(self, "_wide"):
+            self._wide = self.query()["smem_bytes"] == 0
+        return self._wide
+
     def set_wide_core(self, core):
         """Wide path GEMM core: "tf32" (tcgen05, default) or "ffma" (FP32, exact)."""
         _lib.check(self.lib.mafb200_set_wide_core(self._h, {"ffma": 0, "tf32": 1}[core]))

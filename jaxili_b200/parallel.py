@@ -9,6 +9,8 @@ bit-identical.  log_prob evaluation and sampling shard by rows / observations wi
 
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -68,6 +70,8 @@ def setup_peer_allreduce(engine, step):
     rank, world = world_info()
     if world == 1 or world > 8 or engine.n_params * 4 > PEER_ALLREDUCE_MAX_BYTES:
         return False
+    if os.environ.get("MAFB200_NO_PEER"):        # force the NCCL path (A/B measurements)
+        return False
     if not getattr(engine, "_dp_ready", False):
         handle = engine.dp_init(rank, world)
         handles = [None] * world
@@ -83,3 +87,11 @@ def setup_peer_allreduce(engine, step):
         engine.dp_bind_step(step)
         dist.barrier()
     return True
+
+
+def reset_peer_epochs(engine):
+    """Collective: forget the exchange epochs seen so far (the device step counter was rewound)."""
+    torch.cuda.synchronize()
+    dist.barrier()
+    engine.dp_reset()
+    dist.barrier()

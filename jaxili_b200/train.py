@@ -120,6 +120,134 @@ class ResidentLoader:
             yield [theta[s], x[s]]
 
 
+class HostBatchPipeline:
+    """Streams host batches through the fused step without ever idling the GPU on the host.
+
+    The reference's epoch loop hands numpy batches to a jitted step and relies on JAX's asynchronous
+    dispatch, reading the loss once per epoch (jaxili/train.py:427-451).  The same contract here:
+      * two device batch buffers; the H2D copy of batch i+1 runs on a copy stream while the compute stream
+        executes step i (events order buffer reuse in both directions);
+      * the step (flow fwd+bwd, reduce, [peer all-reduce], clip+Adam) is one CUDA graph per buffer;
+      * every step's loss is copied D2H into a pinned ring right behind the step; the host reads the ring
+        after ``drain()`` (one synchronisation per epoch, like ``.item()`` at train.py:449).
+    Batches that are pinned torch tensors are copied from where they lie; anything else goes through a ring
+    of pinned staging buffers whose reuse is guarded by the copy events (no host/DMA race)."""
+
+    N_STAGE = 4
+
+    def __init__(self, trainer, rows):
+        self.t, self.rows = trainer, rows
+        eng = trainer.model.engine()
+        self.eng, dev = eng, eng.device
+        state = trainer.state
+        _, world = parallel.world_info()
+        self.peer = world > 1 and parallel.setup_peer_allreduce(eng, state.step)
+        if world > 1 and not self.peer:
+            raise NotImplementedError("the streamed step under torch.distributed needs the peer-memory all-reduce")
+        self.use_graph = not eng.wide
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.xd = [torch.zeros(rows, eng.n_in, **f32) for _ in range(2)]
+        self.yd = [torch.zeros(rows, max(eng.n_cond, 1), **f32) for _ in range(2)]
+        self.stage = [(torch.empty(rows, eng.n_in, dtype=torch.float32).pin_memory(),
+                       torch.empty(rows, max(eng.n_cond, 1), dtype=torch.float32).pin_memory())
+                      for _ in range(self.N_STAGE)]
+        self.stage_free = [None] * self.N_STAGE
+        self.copy_stream, self.comp_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.h2d_done = [torch.cuda.Event() for _ in range(2)]
+        self.buf_free = [torch.cuda.Event() for _ in range(2)]
+        self.ring = torch.zeros(4096, dtype=torch.float32).pin_memory()
+        self.i = self.base = 0
+        flat = state.params.flat
+        P = flat.numel()
+        self.flat, self.grad, self.loss = flat, trainer._gbuf[:P], trainer._gbuf[-4:-3]
+        self.inv = 1.0 / (rows * world)
+        cur = torch.cuda.current_stream(dev)
+        self.comp_stream.wait_stream(cur)
+        self.copy_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comp_stream):
+            eng.pack(flat)
+            if self.use_graph:
+                # one throw-away launch outside capture (lazy module load), on a copy of the optimiser state
+                keep = [t.clone() for t in (flat, state.opt_state["m"], state.opt_state["v"], state.step)
+                        if t is not None]
+                self._body(0)
+                self.comp_stream.synchronize()
+                for t, k in zip([t for t in (flat, state.opt_state["m"], state.opt_state["v"], state.step)
+                                 if t is not None], keep):
+                    t.copy_(k)
+                eng.pack(flat)
+                if self.peer:
+                    parallel.reset_peer_epochs(eng)      # the step counter was rewound
+                self.graphs = []
+                for b in range(2):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self.comp_stream):
+                        self._body(b)
+                    self.graphs.append(g)
+            for b in range(2):
+                self.buf_free[b].record(self.comp_stream)
+        trainer._packed = True
+
+    def _body(self, b):
+        eng, st = self.eng, self.t.state
+        y = self.yd[b] if eng.n_cond else None
+        eng.loss_grad(self.flat, self.xd[b], y, self.loss, self.grad, inv_global_b=self.inv,
+                      packed_current=True, dp_slot=self.peer)
+        if self.peer:
+            eng.dp_allreduce(self.grad, self.loss)
+        eng.clip_adam(self.flat, self.grad, st.opt_state["m"], st.opt_state["v"], st.step, st.tx,
+                      norm_current=True)
+
+    def _source(self, a, which):
+        """A pinned host view of ``a`` [rows, cols]: the tensor itself if it already is pinned, else a staging copy."""
+        if isinstance(a, torch.Tensor) and a.dtype == torch.float32 and a.is_pinned() and a.is_contiguous():
+            return a.reshape(self.rows, -1), None
+        k = self.i % self.N_STAGE
+        if which == 0 and self.stage_free[k] is not None:
+            self.stage_free[k].synchronize()          # the DMA that last read this staging slot has finished
+        dst = self.stage[k][which]
+        src = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float32)
+        dst.numpy()[...] = src.reshape(dst.shape)
+        return dst, k
+
+    def submit(self, batch):
+        xb, yb = self.t._batch_xy(batch)
+        b = self.i & 1
+        sx, kx = self._source(xb, 0)
+        sy, ky = self._source(yb, 1) if self.eng.n_cond else (None, None)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.buf_free[b])       # step i-2 no longer reads this device buffer
+            self.xd[b].copy_(sx, non_blocking=True)
+            if sy is not None:
+                self.yd[b].copy_(sy, non_blocking=True)
+            self.h2d_done[b].record(self.copy_stream)
+        if kx is not None or ky is not None:
+            k = kx if kx is not None else ky
+            if self.stage_free[k] is None:
+                self.stage_free[k] = torch.cuda.Event()
+            self.stage_free[k].record(self.copy_stream)
+        with torch.cuda.stream(self.comp_stream):
+            self.comp_stream.wait_event(self.h2d_done[b])
+            if self.use_graph:
+                self.graphs[b].replay()
+            else:
+                self._body(b)
+            slot = self.i - self.base
+            if slot >= self.ring.numel():
+                raise RuntimeError("loss ring full: call drain() at least every 4096 steps")
+            self.ring[slot:slot + 1].copy_(self.loss, non_blocking=True)     # D2H read of this step's loss
+            self.buf_free[b].record(self.comp_stream)
+        self.i += 1
+
+    def drain(self):
+        """Wait for everything submitted; returns the per-step losses since the previous drain (numpy)."""
+        self.comp_stream.synchronize()
+        out = self.ring[: self.i - self.base].numpy().copy()
+        self.base = self.i
+        torch.cuda.current_stream(self.eng.device).wait_stream(self.comp_stream)
+        return out
+
+
 class TrainerModule:
     """Training loop, evaluation, logging and checkpointing around the fused kernels."""
 
@@ -151,6 +279,8 @@ class TrainerModule:
         self.create_jitted_functions()
         self.init_model(self.exmp_input)
         self._bufs = {}
+        self._buf_events = {}
+        self._pipeline = None
 
     # ------------------------------------------------------------------ setup
     def init_logger(self, logger_params: Optional[Dict] = None):
@@ -261,8 +391,14 @@ class TrainerModule:
             self._bufs[key] = (torch.empty(a.shape, dtype=torch.float32).pin_memory(),
                                torch.empty(a.shape, dtype=torch.float32, device=eng.device))
         pin, dev = self._bufs[key]
+        ev = self._buf_events.get(key)
+        if ev is not None:
+            ev.synchronize()                   # the previous H2D out of this staging buffer has finished
+        else:
+            ev = self._buf_events[key] = torch.cuda.Event()
         pin.numpy()[...] = a
         dev.copy_(pin, non_blocking=True)
+        ev.record()
         return dev
 
     def _batch_xy(self, batch):
@@ -410,6 +546,8 @@ class TrainerModule:
         metrics = defaultdict(float)
         num_train_steps = len(train_loader)
         start_time = time.time()
+        if self._streamable():
+            return self._train_epoch_streamed(train_loader, num_train_steps, start_time)
         for batch in train_loader:
             self.state, step_metrics = self.train_step(self.state, batch)
             for key in step_metrics:
@@ -418,6 +556,53 @@ class TrainerModule:
                    for key in metrics}
         metrics["epoch_time"] = time.time() - start_time
         return metrics
+
+    def _streamable(self):
+        """The pipelined epoch serves the stock step only: a subclass that overrides ``create_functions``
+        (jaxili/train.py:317-328 invites that) or a non-NLL loss keeps the plain loop."""
+        if getattr(self, "stream_host_batches", True) is False or self.state is None or self.state.tx is None:
+            return False
+        if type(self).create_functions is not TrainerModule.create_functions:
+            return False
+        try:
+            self._batch_xy([None, None])
+        except NotImplementedError:
+            return False
+        _, world = parallel.world_info()
+        eng = self.model.engine()
+        return world == 1 or (not eng.wide and parallel.setup_peer_allreduce(eng, self.state.step))
+
+    def host_pipeline(self, rows):
+        """The (cached) ``HostBatchPipeline`` for batches of ``rows`` rows and the current optimiser state."""
+        p = self._pipeline
+        if p is None or p.rows != rows or p.t.state is not self.state or p.flat is not self.state.params.flat:
+            p = self._pipeline = HostBatchPipeline(self, rows)
+        return p
+
+    def _train_epoch_streamed(self, train_loader, num_train_steps, start_time):
+        pipe, total, n = None, 0.0, 0
+        for batch in train_loader:
+            first = batch[0]
+            rows = first.shape[0]
+            if isinstance(first, torch.Tensor) and first.is_cuda:
+                # device-resident batches need no staging: plain step
+                if pipe is not None:
+                    total += float(pipe.drain().sum())
+                self.state, m = self.train_step(self.state, batch)
+                total += float(m["loss"].item())
+                n += 1
+                continue
+            if pipe is None or pipe.rows != rows:
+                if pipe is not None:
+                    total += float(pipe.drain().sum())
+                pipe = self.host_pipeline(rows)
+            if pipe.i - pipe.base >= pipe.ring.numel():
+                total += float(pipe.drain().sum())
+            pipe.submit(batch)
+            n += 1
+        if pipe is not None:
+            total += float(pipe.drain().sum())
+        return {"train/loss": total / max(num_train_steps, 1), "epoch_time": time.time() - start_time}
 
     def eval_model(self, data_loader: Iterator, log_prefix: Optional[str] = "") -> Dict[str, Any]:
         """jaxili/train.py:453-487: size-weighted mean over the batches."""

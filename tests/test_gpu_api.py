@@ -164,6 +164,45 @@ def test_graph_step_equals_eager_steps(tmp_path):
     assert torch.allclose(a.state.params.flat, b.state.params.flat, rtol=0, atol=1e-6)
 
 
+def test_streamed_epoch_equals_plain_steps(tmp_path):
+    """train_epoch over HOST batches (double-buffered H2D on a copy stream, one CUDA graph per buffer, loss
+    ring read once per epoch) == the plain train_step loop, bit for bit; numpy and pinned-tensor batches."""
+    from jaxili_b200 import nn
+    from jaxili_b200.loss import loss_nll_nle, loss_nll_npe
+    from jaxili_b200.model import ConditionalMAF, Identity, NDE_w_Standardization, ScalarAffine, Sequential, Standardizer
+    from jaxili_b200.train import TrainerModule
+    theta, x = _sim(11 * 256, seed=8)
+
+    def mk(loss, stream):
+        d_in, d_c = (theta, x) if loss is loss_nll_npe else (x, theta)
+        maf = ConditionalMAF(10, 10, 5, [50, 50], activation=nn.relu, use_reverse=True, seed=42)
+        hp = {"nde": maf, "embedding_net": Sequential([Standardizer(d_c.mean(0), d_c.std(0)), Identity()]),
+              "transformation": ScalarAffine(shift=d_in.mean(0), scale=d_in.std(0))}
+        tr = TrainerModule(NDE_w_Standardization, hp, {"lr": 1e-3, "warmup": 0.1}, loss,
+                           (np.zeros((1, 10), np.float32), np.zeros((1, 10), np.float32)),
+                           logger_params={"base_log_dir": str(tmp_path)}, enable_progress_bar=False,
+                           nde_class="NPE" if loss is loss_nll_npe else "NLE")
+        tr.init_optimizer(10, 11)
+        tr.stream_host_batches = stream
+        return tr
+
+    np_loader = [[theta[i * 256:(i + 1) * 256], x[i * 256:(i + 1) * 256]] for i in range(11)]
+    pin_loader = [[torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()] for a, b in np_loader]
+    for loss in (loss_nll_npe, loss_nll_nle):
+        plain, s_np, s_pin = mk(loss, False), mk(loss, True), mk(loss, True)
+        outs = []
+        for tr, loader in ((plain, np_loader), (s_np, np_loader), (s_pin, pin_loader)):
+            m1 = tr.train_epoch(loader)
+            m2 = tr.train_epoch(loader)            # the second epoch reuses the pipeline
+            outs.append((m1["train/loss"], m2["train/loss"], tr.state.params.flat.clone(), int(tr.state.step.item())))
+        assert s_np._pipeline is not None and plain._pipeline is None
+        for o in outs[1:]:
+            assert o[3] == outs[0][3] == 22
+            assert abs(o[0] - outs[0][0]) < 1e-5 and abs(o[1] - outs[0][1]) < 1e-5
+            assert torch.equal(o[2], outs[0][2])
+        assert outs[0][1] < outs[0][0]             # it trains
+
+
 def test_npe_end_to_end(tmp_path):
     """jaxili/tests/test_npe.py:38-220 in one flow: split bookkeeping, loaders, standardisation,
     training smoke test (metrics, files), density estimator and DirectPosterior surface."""
