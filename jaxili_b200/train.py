@@ -128,8 +128,9 @@ class HostBatchPipeline:
       * two device batch buffers; the H2D copy of batch i+1 runs on a copy stream while the compute stream
         executes step i (events order buffer reuse in both directions);
       * the step (flow fwd+bwd, reduce, [peer all-reduce], clip+Adam) is one CUDA graph per buffer;
-      * every step's loss is copied D2H into a pinned ring right behind the step; the host reads the ring
-        after ``drain()`` (one synchronisation per epoch, like ``.item()`` at train.py:449).
+      * every step's loss is copied D2H into a pinned ring right behind the step, on a third stream so the
+        4-byte copy's latency never sits between two steps (each graph owns its loss word); the host reads
+        the ring after ``drain()`` (one synchronisation per epoch, like ``.item()`` at train.py:449).
     Batches that are pinned torch tensors are copied from where they lie; anything else goes through a ring
     of pinned staging buffers whose reuse is guarded by the copy events (no host/DMA race)."""
 
@@ -153,13 +154,16 @@ class HostBatchPipeline:
                       for _ in range(self.N_STAGE)]
         self.stage_free = [None] * self.N_STAGE
         self.copy_stream, self.comp_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.d2h_stream = torch.cuda.Stream(device=dev)
         self.h2d_done = [torch.cuda.Event() for _ in range(2)]
         self.buf_free = [torch.cuda.Event() for _ in range(2)]
+        self.loss_read = [torch.cuda.Event() for _ in range(2)]
+        self.loss_b = [torch.zeros(1, **f32) for _ in range(2)]
         self.ring = torch.zeros(4096, dtype=torch.float32).pin_memory()
         self.i = self.base = 0
         flat = state.params.flat
         P = flat.numel()
-        self.flat, self.grad, self.loss = flat, trainer._gbuf[:P], trainer._gbuf[-4:-3]
+        self.flat, self.grad = flat, trainer._gbuf[:P]
         self.inv = 1.0 / (rows * world)
         cur = torch.cuda.current_stream(dev)
         self.comp_stream.wait_stream(cur)
@@ -186,15 +190,16 @@ class HostBatchPipeline:
                     self.graphs.append(g)
             for b in range(2):
                 self.buf_free[b].record(self.comp_stream)
+                self.loss_read[b].record(self.comp_stream)
         trainer._packed = True
 
     def _body(self, b):
         eng, st = self.eng, self.t.state
         y = self.yd[b] if eng.n_cond else None
-        eng.loss_grad(self.flat, self.xd[b], y, self.loss, self.grad, inv_global_b=self.inv,
+        eng.loss_grad(self.flat, self.xd[b], y, self.loss_b[b], self.grad, inv_global_b=self.inv,
                       packed_current=True, dp_slot=self.peer)
         if self.peer:
-            eng.dp_allreduce(self.grad, self.loss)
+            eng.dp_allreduce(self.grad, self.loss_b[b])
         eng.clip_adam(self.flat, self.grad, st.opt_state["m"], st.opt_state["v"], st.step, st.tx,
                       norm_current=True)
 
@@ -226,25 +231,31 @@ class HostBatchPipeline:
             if self.stage_free[k] is None:
                 self.stage_free[k] = torch.cuda.Event()
             self.stage_free[k].record(self.copy_stream)
+        slot = self.i - self.base
+        if slot >= self.ring.numel():
+            raise RuntimeError("loss ring full: call drain() at least every 4096 steps")
         with torch.cuda.stream(self.comp_stream):
             self.comp_stream.wait_event(self.h2d_done[b])
+            self.comp_stream.wait_event(self.loss_read[b])      # step i-2's loss word has been copied out
             if self.use_graph:
                 self.graphs[b].replay()
             else:
                 self._body(b)
-            slot = self.i - self.base
-            if slot >= self.ring.numel():
-                raise RuntimeError("loss ring full: call drain() at least every 4096 steps")
-            self.ring[slot:slot + 1].copy_(self.loss, non_blocking=True)     # D2H read of this step's loss
             self.buf_free[b].record(self.comp_stream)
+        with torch.cuda.stream(self.d2h_stream):
+            self.d2h_stream.wait_event(self.buf_free[b])
+            self.ring[slot:slot + 1].copy_(self.loss_b[b], non_blocking=True)   # D2H read of this step's loss
+            self.loss_read[b].record(self.d2h_stream)
         self.i += 1
 
     def drain(self):
         """Wait for everything submitted; returns the per-step losses since the previous drain (numpy)."""
         self.comp_stream.synchronize()
+        self.d2h_stream.synchronize()
         out = self.ring[: self.i - self.base].numpy().copy()
         self.base = self.i
         torch.cuda.current_stream(self.eng.device).wait_stream(self.comp_stream)
+        self.t._gbuf[-4:-3].copy_(self.loss_b[(self.i - 1) & 1])      # where the plain step leaves its loss
         return out
 
 
