@@ -128,6 +128,19 @@ __device__ __forceinline__ void act_eval(int act, float a, float& h, float& d) {
 // row pitch RP (RP/4 odd, so consecutive feature rows start 16 bytes apart modulo 128).
 
 // out[c][r] = sum_q in[q][r] * m[q][c]   for r in r0..r0+TM-1, c in c0..c0+TN-1
+#ifndef MAFB_FFMA2
+#define MAFB_FFMA2 1
+#endif
+// (d0, d1) += (a0, a1) * (b0, b1): sm_100 packed FP32 FMA (SASS FFMA2).  ptxas keeps the operands in aligned
+// register pairs (they come from 128-bit shared-memory loads) and folds b0 == b1 into a scalar-broadcast operand.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 // in: [Q][RP] feature-major, m: [Q][CP] row-major.  Per q: one TM-wide and one TN-wide vector
 // load feed TM*TN FFMAs.  Only q = q0, q0+qs, q0+2qs, ... are visited (lane-group split of the
 // reduction; qs = 1 for the whole sum).
@@ -149,10 +162,20 @@ __device__ __forceinline__ void mm_outer_acc(float (&acc)[TN][TM], const float* 
     ldv(wv, w);
     a += da;
     w += dw;
+#if MAFB_FFMA2
+    // packed FFMA2: two accumulators along the row pair per instruction, the weight as a scalar broadcast
+    // operand -- same FP32 FMA rate as FFMA with half the issue slots (tests/micro/ffma2_peak.cu), bit-identical
+    static_assert(TM % 2 == 0, "row tile must be even for the packed form");
+#pragma unroll
+    for (int j = 0; j < TN; ++j)
+#pragma unroll
+      for (int i = 0; i < TM; i += 2) ffma2(acc[j][i], acc[j][i + 1], av[i], av[i + 1], wv[j], wv[j]);
+#else
 #pragma unroll
     for (int j = 0; j < TN; ++j)
 #pragma unroll
       for (int i = 0; i < TM; ++i) acc[j][i] = fmaf(av[i], wv[j], acc[j][i]);
+#endif
   }
 }
 
@@ -212,6 +235,9 @@ __device__ __forceinline__ void mm_inner_rs2(const float* __restrict__ A, int K,
                                              int nKB, int nb, int nNB, int rh, bool store,
                                              float* __restrict__ out, bool accumulate) {
   float acc[4][4];
+#if MAFB_FFMA2
+  float acc_odd[4][4];
+#endif
   const float* ap[4];
   const float* gp[4];
 #pragma unroll
@@ -219,7 +245,12 @@ __device__ __forceinline__ void mm_inner_rs2(const float* __restrict__ A, int K,
     const int k = kb + i * nKB;
     ap[i] = A + (k < K ? k : ones_row) * RP + 4 * rh;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) {
+      acc[i][j] = 0.f;
+#if MAFB_FFMA2
+      acc_odd[i][j] = 0.f;
+#endif
+    }
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -233,13 +264,30 @@ __device__ __forceinline__ void mm_inner_rs2(const float* __restrict__ A, int K,
     for (int i = 0; i < 4; ++i) { ldv(av[i], ap[i]); ap[i] += 8; }
 #pragma unroll
     for (int j = 0; j < 4; ++j) { ldv(gv[j], gp[j]); gp[j] += 8; }
+#if MAFB_FFMA2
+    // packed FFMA2 over the row pairs (t, t+1): even rows accumulate in acc, odd rows in acc_odd
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int t = 0; t < 4; t += 2)
+          ffma2(acc[i][j], acc_odd[i][j], av[i][t], av[i][t + 1], gv[j][t], gv[j][t + 1]);
+#else
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int t = 0; t < 4; ++t) acc[i][j] = fmaf(av[i][t], gv[j][t], acc[i][j]);
+#endif
   }
+#if MAFB_FFMA2
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] += acc_odd[i][j];
+#endif
   // reduce-scatter across the half-warps: keep tile rows 2rh, 2rh+1
   float res[2][4];
 #pragma unroll

@@ -205,6 +205,10 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
       const bool last = i == n_lin - 1;
       float* hout = last ? obuf : slot + P.h_off[i + 1];
       float* dout = slot + P.d_off[last ? 1 : i + 1];
+      const float* xin_k = sm + P.o_xin + k * P.xin_stride;
+      float* xnext = (k + 1 < L) ? sm + P.o_xin + (k + 1) * P.xin_stride : gu;
+      float* sbuf = slot + P.s_off;
+      float* vbuf = slot + P.v_off;
       for (int blk = warp; blk < A.ph[i].fB; blk += NW) {
         const int cb = blk * o_cpw + o_cbl;
         const bool ok = o_rok && cb < nCB;
@@ -216,21 +220,46 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
         reduce_scatter2(acc, kq, res);
         stamp(32);
         if (ok) {   // half-warp kq finishes tile columns 2kq, 2kq+1
+          if (!last) {
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int c = c0 + 2 * kq + cc;
-            const float bj = bias[c];
-            if (!last) {
+            for (int cc = 0; cc < 2; ++cc) {
+              const int c = c0 + 2 * kq + cc;
+              const float bj = bias[c];
               float hv[TS], dv[TS];
 #pragma unroll
               for (int q = 0; q < TS; ++q) act_eval<RELU>(P.act, res[cc][q] + bj, hv[q], dv[q]);
               stv(hout + c * RP + o_r0, hv);
               if (!RELU && BWD) stv(dout + c * RP + o_r0, dv);
-            } else {
-              float ov[TS];
+            }
+          } else {
+            // the last linear's image interleaves (mu_j, logp_j): this thread holds both for feature j and
+            // applies the affine autoregressive transform (jaxili/model.py:739-742) right here
+            const int c = c0 + 2 * kq;
+            const int j = c >> 1;
+            if (j < D) {
+              const float bm = bias[c], bl = bias[c + 1];
+              float xv[TS], sv[TS], vv[TS];
+              ldv(xv, xin_k + j * RP + o_r0);
 #pragma unroll
-              for (int q = 0; q < TS; ++q) ov[q] = res[cc][q] + bj;
-              stv(hout + c * RP + o_r0, ov);
+              for (int q = 0; q < TS; ++q) {
+                const float lp = res[1][q] + bl;
+                sv[q] = expf(0.5f * lp);
+                vv[q] = (xv[q] - (res[0][q] + bm)) * sv[q];
+                res[1][q] = 0.5f * lp;
+              }
+              if (BWD) {
+                stv(sbuf + j * RP + o_r0, sv);
+                stv(vbuf + j * RP + o_r0, vv);
+              }
+              if (!replay) {
+                float lv[TS];
+                ldv(lv, ld + j * RP + o_r0);
+#pragma unroll
+                for (int q = 0; q < TS; ++q) lv[q] += res[1][q];
+                stv(ld + j * RP + o_r0, lv);
+                const int jj = P.reverse ? D - 1 - j : j;
+                stv(xnext + jj * RP + o_r0, vv);
+              }
             }
           }
         }
@@ -240,25 +269,6 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
       __syncthreads();
       stamp(10 + i);
     }
-    // affine autoregressive transform (jaxili/model.py:739-742): lane = row, warp strides features
-    const float* xin = sm + P.o_xin + k * P.xin_stride;
-    float* xnext = (k + 1 < L) ? sm + P.o_xin + (k + 1) * P.xin_stride : gu;
-    float* sbuf = slot + P.s_off;
-    float* vbuf = slot + P.v_off;
-    for (int r = lane; r < Rt; r += 32)
-      for (int j = warp; j < D; j += NW) {
-        const float mu = obuf[j * RP + r], lp = obuf[(D + j) * RP + r];
-        const float s = expf(0.5f * lp);
-        const float v = (xin[j * RP + r] - mu) * s;
-        if (BWD) { sbuf[j * RP + r] = s; vbuf[j * RP + r] = v; }
-        if (!replay) {
-          ld[j * RP + r] += 0.5f * lp;
-          const int jj = P.reverse ? D - 1 - j : j;
-          xnext[jj * RP + r] = v;
-        }
-      }
-    __syncthreads();
-    stamp(19);
   };
 
   for (int ti = 0; ti < my_n; ++ti) {
@@ -347,8 +357,12 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
         float* pg = pg_cta + (size_t)k * P.ppl;
         const float* xin = sm + P.o_xin + k * P.xin_stride;
 
-        // gradient w.r.t. the MADE outputs (mu | logp) and the direct path to x
-        {
+        // gradient w.r.t. the MADE outputs (mu | logp) and the direct path to x.  With every layer's (s, v)
+        // stashed this runs as its own phase for the last layer only: for the others it is fused into the
+        // epilogue of the following layer's input-gradient product (below).
+        const bool fuse_ew = P.stash_all != 0;
+        float* gx_k = gx + (k & 1) * P.DP * RP;
+        if (!fuse_ew || k == L - 1) {
           const float* sbuf = slot + P.s_off;
           const float* vbuf = slot + P.v_off;
           for (int r = lane; r < Rt; r += 32) {
@@ -359,12 +373,12 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
               const float s = sbuf[j * RP + r], v = vbuf[j * RP + r];
               obuf[j * RP + r] = ok ? -gv * s : 0.f;
               obuf[(D + j) * RP + r] = ok ? 0.5f * gv * v - 0.5f * A.inv_b : 0.f;
-              gx[j * RP + r] = ok ? gv * s : 0.f;
+              gx_k[j * RP + r] = ok ? gv * s : 0.f;
             }
           }
+          __syncthreads();
+          stamp(5);
         }
-        __syncthreads();
-        stamp(5);
 
 #pragma unroll
         for (int ii = 0; ii < (NLIN > 0 ? NLIN : MAFB_MAX_LIN); ++ii) {
@@ -402,10 +416,29 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
                       gv[q] = RELU ? (dv[q] > 0.f ? res[cc][q] : 0.f) : res[cc][q] * dv[q];
                     stv(sm + P.o_g[(i - 1) & 1] + c * RP + o_r0, gv);
                   } else if (c < D || !A.out_dy) {   // gradient w.r.t. this layer's input x: MADE + direct path
-                    ldv(dv, gx + c * RP + o_r0);
+                    ldv(dv, gx_k + c * RP + o_r0);
 #pragma unroll
                     for (int q = 0; q < TS; ++q) gv[q] = res[cc][q] + dv[q];
-                    stv(gu + c * RP + o_r0, gv);
+                    if (!fuse_ew) {
+                      stv(gu + c * RP + o_r0, gv);
+                    } else if (k > 0 && c < D) {
+                      // x_k is layer k-1's (flipped) output: continue straight into that layer's elementwise step
+                      const int j = P.reverse ? D - 1 - c : c;
+                      const float* pslot = sm + P.o_slot + (k - 1) * P.slot_stride;
+                      float sv[TS], vv[TS], o0[TS], o1[TS], gn[TS];
+                      ldv(sv, pslot + P.s_off + j * RP + o_r0);
+                      ldv(vv, pslot + P.v_off + j * RP + o_r0);
+#pragma unroll
+                      for (int q = 0; q < TS; ++q) {
+                        const bool okr = o_r0 + q < valid;
+                        o0[q] = okr ? -gv[q] * sv[q] : 0.f;
+                        o1[q] = okr ? 0.5f * gv[q] * vv[q] - 0.5f * A.inv_b : 0.f;
+                        gn[q] = okr ? gv[q] * sv[q] : 0.f;
+                      }
+                      stv(obuf + j * RP + o_r0, o0);
+                      stv(obuf + (D + j) * RP + o_r0, o1);
+                      stv(gx + ((k - 1) & 1) * P.DP * RP + j * RP + o_r0, gn);
+                    }
                   } else if (c < P.K0) {             // dy mode, conditioner columns: summed over the layers
                     float* gyp = sm + P.o_gy + (c - D) * RP + o_r0;
                     ldv(dv, gyp);

@@ -173,7 +173,7 @@ bool plan_layout(Plan& P, int R, bool stash_all, int n_wbuf, int limit) {
   P.o_gu = o;
   o += P.DP * RP;
   P.o_gx = o;
-  o += P.DP * RP;
+  o += 2 * P.DP * RP;                     // ping-pong by layer parity (fused reverse elementwise step)
   P.o_ld = o;
   o += P.DP * RP;
   P.o_cst = o;

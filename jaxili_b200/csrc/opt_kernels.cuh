@@ -46,10 +46,14 @@ __device__ __forceinline__ void write_image(const Plan& P, float* wimg, int idx,
   const bool is_bias = decode_param(P, idx, layer, li, k, n);
   const LinDesc& ln = P.lin[li];
   float* base = wimg + (size_t)layer * P.img_floats;
+  // forward image of the LAST linear: output columns interleaved (mu_j, logp_j) -> (2j, 2j+1), so that one
+  // thread's 4-column tile holds both halves of a feature and the affine transform runs in the epilogue.
+  // The transposed (reverse-pass) image keeps the parameter order.
+  const int nf = (li == P.n_lin - 1) ? (n < P.D ? 2 * n : 2 * (n - P.D) + 1) : n;
   if (is_bias) {
-    base[ln.b_off + n] = masked_value;
+    base[ln.b_off + nf] = masked_value;
   } else {
-    base[ln.w_off + k * ln.NP + n] = masked_value;
+    base[ln.w_off + k * ln.NP + nf] = masked_value;
     base[P.fwd_floats + ln.wt_off + n * ln.KP + k] = masked_value;
   }
 }

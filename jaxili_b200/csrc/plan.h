@@ -41,7 +41,7 @@ struct Plan {
   int d_off[MAFB_MAX_LIN];      // slot-relative offset of act'(a_i) (need_d only)
   int s_off, v_off;             // slot-relative exp(logp/2) and v=(x-mu)s, [DP][RP] each
   int o_obuf;                   // [round4(2D)][RP]: MADE output, then grad wrt it
-  int o_gu, o_gx, o_ld;         // [DP][RP] each
+  int o_gu, o_gx, o_ld;         // [DP][RP] each (o_gx: two of them, ping-pong by layer parity)
   int o_cst;                    // standardisation constants [2D + 2C]
   int o_gy;                     // [round4(C)][RP]: gradient w.r.t. the standardised conditioner (dy mode)
   int o_g[2];                   // ping-pong [max HP][RP] hidden-gradient buffers
