@@ -445,7 +445,7 @@ def main():
             launches_per_step = 10 * (3 + 1 + 1 + 3 * 3 + 1) + 6
         elif world == 1:
             step_fn = trainer.make_graph_step(theta_d, x_d, batch)
-            launches_per_step = 3          # flow, reduce, clip_adam
+            launches_per_step = 2          # flow kernel, cooperative tail (reduce + norm + clip + Adam + re-pack)
         else:
             state = trainer.state
             xd, yd = trainer._batch_xy([theta_d, x_d])

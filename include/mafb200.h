@@ -17,6 +17,7 @@
  *                                jaxili/posterior/mcmc_posterior.py:139-159, 194-201
  *   mafb200_hmc_trajectory    <- numpyro HMC leapfrog integration inside MCMCPosterior.sample
  *                                jaxili/posterior/mcmc_posterior.py:78-118, 248-305
+ *   mafb200_train_step        <- TrainerModule.create_functions().train_step    jaxili/train.py:330-335
  *   mafb200_clip_adam         <- state.apply_gradients(grads) with the optax chain built in
  *                                jaxili/train.py:246-300 (clip_by_global_norm -> adam(warmup_cosine))
  *   mafb200_forward           <- ConditionalMAF.__call__ (u, log_det)  jaxili/model.py:848-874
@@ -220,6 +221,15 @@ int mafb200_log_prob_grad_y(mafb200_handle h, const float* params, const float* 
    _nuts_numpyro, jaxili/posterior/mcmc_posterior.py:194-305. */
 int mafb200_hmc_trajectory(mafb200_handle h, const float* params, const float* x, int64_t n,
                            const MafHmcState* state, int32_t n_steps, int32_t flags, void* stream);
+
+/* The whole single-rank step in one call: train_step of jaxili/train.py:330-335 (value_and_grad of the NLL +
+   state.apply_gradients).  Same arguments as loss_grad followed by clip_adam; out_loss / out_grad receive the
+   step's loss and (unclipped) gradient, params / m / v / step are updated in place.  On narrow models the
+   tail (gradient reduction, norm, clip, Adam, re-pack) is a single cooperative kernel. */
+int mafb200_train_step(mafb200_handle h, float* params, const float* x, const float* y, int64_t B,
+                       float inv_global_B, const int32_t* batch_index, int64_t n_batches, float* out_loss,
+                       float* out_grad, float* m, float* v, int32_t* step, const MafOptDesc* opt, int32_t flags,
+                       void* stream);
 
 /* optax.chain(clip_by_global_norm, adam(schedule)) + apply_gradients, in place on
    params / m / v; step[0] (device int32) is the optax count and is incremented.

@@ -84,6 +84,9 @@ SYMBOLS = {
                                           C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mafb200_hmc_trajectory": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(MafHmcState),
                                          C.c_int32, C.c_int32, C.c_void_p]),
+    "mafb200_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
+                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.POINTER(MafOptDesc), C.c_int32, C.c_void_p]),
     "mafb200_clip_adam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.POINTER(MafOptDesc), C.c_int32, C.c_void_p]),
     "mafb200_sample_from_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -64,6 +64,8 @@ struct mafb200_handle_s {
   float* partial_loss = nullptr;
   float* normpart = nullptr;
   unsigned int* done_counter = nullptr;
+  unsigned long long* grid_bar = nullptr;   // ticket counter of step_tail_kernel's grid barrier
+  int tail_ok = -1;             // step_tail_kernel co-residency (-1: not probed yet)
   float logdet_const = 0.f;
   int n_norm = 0;
   long long* trace = nullptr;   // debug: device buffer of 1001 int64 (set by mafb200_debug_trace)
@@ -707,6 +709,8 @@ int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shi
   CUH(cudaMemset(h->normpart, 0, h->n_norm * 4));
   CUH(cudaMalloc(&h->done_counter, 4));
   CUH(cudaMemset(h->done_counter, 0, 4));
+  CUH(cudaMalloc(&h->grid_bar, 8));
+  CUH(cudaMemset(h->grid_bar, 0, 8));
 
   if (have_sampler) {
     // degree-sorted positions and group tables
@@ -798,6 +802,7 @@ int mafb200_destroy(mafb200_handle h) {
   cudaFree(h->partial_loss);
   cudaFree(h->normpart);
   cudaFree(h->done_counter);
+  cudaFree(h->grid_bar);
   for (int r = 0; r < h->dp_world; ++r)
     if (r != h->dp_rank && h->dp_peer_sym[r]) cudaIpcCloseMemHandle(h->dp_peer_sym[r]);
   cudaFree(h->dp_sym);
@@ -1233,6 +1238,72 @@ int mafb200_hmc_trajectory(mafb200_handle h, const float* params, const float* x
     hmc_kick_kernel<<<bk, 256, 0, st>>>(A);
     CU(cudaGetLastError());
   }
+  return 0;
+}
+
+// TrainerModule.train_step as one call (jaxili/train.py:330-335: value_and_grad + apply_gradients) for a
+// single rank.  Narrow models: the flow kernel followed by ONE cooperative tail kernel (reduction of the
+// partial gradients, global norm, clip, schedule, Adam, re-pack).  Wide models and anything the tail cannot
+// serve fall through to loss_grad + clip_adam, same results.
+int mafb200_train_step(mafb200_handle h, float* params, const float* x, const float* y, int64_t B,
+                       float inv_global_B, const int32_t* batch_index, int64_t n_batches, float* out_loss,
+                       float* out_grad, float* m, float* v, int32_t* step, const MafOptDesc* opt, int32_t flags,
+                       void* stream) {
+  if (!h || !params || !x || (h->desc.n_cond && !y) || !out_loss || !out_grad || !step || !opt)
+    return fail("null argument");
+  if (flags & MAFB200_DP_SLOT) return fail("train_step is the single-rank step; use loss_grad + dp_allreduce + clip_adam");
+  if (opt->kind < 0 || opt->kind > 2) return fail("unknown optimizer kind");
+  if (opt->kind != 1 && (!m || !v)) return fail("adam needs m and v");
+  if (opt->decay_steps - opt->warmup <= 0.f) return fail("cosine_decay_schedule requires positive decay_steps");
+  if (!h->wide && h->tail_ok < 0) {
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_tail_kernel, RED_IDX * RED_PARTS, 0));
+    int coop = 0;
+    CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+    h->tail_ok = (coop && (long long)per_sm * h->n_sm >= h->n_norm) ? 1 : 0;
+  }
+  if (h->wide || h->tail_ok != 1) {
+    if (mafb200_loss_grad(h, params, x, y, B, inv_global_B, batch_index, n_batches, out_loss, out_grad, flags, stream))
+      return 1;
+    return mafb200_clip_adam(h, params, out_grad, m, v, step, opt, MAFB200_NORM_CURRENT, stream);
+  }
+  if (B <= 0) return fail("train_step needs a non-empty batch");
+  if (batch_index && n_batches <= 0) return fail("n_batches must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!(flags & MAFB200_PACKED_CURRENT) && mafb200_pack(h, params, stream)) return 1;
+  FlowArgs A{};
+  A.wimg = h->wimg;
+  A.x = x;
+  A.y = y;
+  A.B = B;
+  A.batch_index = batch_index;
+  A.n_batches = batch_index ? n_batches : 1;
+  A.stdc = h->stdc;
+  A.logdet_const = h->logdet_const;
+  A.inv_b = inv_global_B;
+  A.trace = h->trace;
+  A.partial_grad = h->partial;
+  A.partial_loss = h->partial_loss;
+  int grid;
+  const Plan* pp;
+  if (launch_geometry(h, B, pp, A.Rt, A.n_tiles, grid)) return 1;
+  fill_phases(*pp, A);
+  if (h->timing && flow_timing_begin(h, st)) return 1;
+  launch_flow<true>(*pp, A, grid, st);
+  CU(cudaGetLastError());
+  if (h->timing) CU(cudaEventRecord(h->ev1, st));
+  OptArgs O{opt->lr, opt->warmup, opt->decay_steps, opt->init_factor, opt->end_factor, opt->b1, opt->b2,
+            opt->eps, opt->clip, opt->weight_decay, opt->kind};
+  Plan Pk = h->plan;           // image layout and parameter count (shared by both occupancy plans)
+  const float* partial = h->partial;
+  const unsigned char* mask = h->mask;
+  const float* ploss = h->partial_loss;
+  float* normpart = h->normpart;
+  float* wimg = h->wimg;
+  unsigned long long* bar = h->grid_bar;
+  void* args[] = {&Pk, &O, &partial, &grid, &mask, &out_grad, &ploss, &out_loss, &normpart, &params,
+                  &m, &v, &step, &wimg, &bar};
+  CU(cudaLaunchCooperativeKernel((const void*)step_tail_kernel, dim3(h->n_norm), dim3(RED_IDX * RED_PARTS), args, 0, st));
   return 0;
 }
 

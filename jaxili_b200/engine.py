@@ -264,6 +264,28 @@ class MafEngine:
         o.kind = {"adam": 0, "sgd": 1, "adamw": 2}[kind]
         return o
 
+    def train_step(self, params, x, y, out_loss, out_grad, m, v, step, opt, batch_rows=None, inv_global_b=None,
+                   batch_index=None, n_batches=1, packed_current=False):
+        """loss_grad + clip_adam as one call (single rank): flow kernel + one cooperative tail kernel."""
+        if step.dtype != torch.int32 or not step.is_cuda:
+            raise TypeError("step must be an int32 CUDA tensor")
+        px = self._chk(x, "x", self.n_in)
+        py = self._chk(y, "y", self.n_cond) if self.n_cond else None
+        B = x.shape[0] if batch_rows is None else int(batch_rows)
+        if batch_index is not None:
+            if x.shape[0] < B * n_batches:
+                raise ValueError("x holds fewer than n_batches * batch_rows rows")
+            bi = C.c_void_p(batch_index.data_ptr())
+        else:
+            bi = None
+        inv = 1.0 / B if inv_global_b is None else float(inv_global_b)
+        _lib.check(self.lib.mafb200_train_step(
+            self._h, self._chk(params, "params"), px, py, B, inv, bi, int(n_batches),
+            self._chk(out_loss, "out_loss"), self._chk(out_grad, "out_grad"),
+            self._chk(m, "m") if m is not None else None, self._chk(v, "v") if v is not None else None,
+            C.c_void_p(step.data_ptr()), C.byref(opt), _lib.PACKED_CURRENT if packed_current else 0,
+            self._stream()))
+
     def clip_adam(self, params, grad, m, v, step, opt, norm_current=False):
         """In-place optax-chain update; ``step`` is an int32 CUDA tensor (the optax count)."""
         if step.dtype != torch.int32 or not step.is_cuda:

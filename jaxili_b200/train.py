@@ -120,6 +120,24 @@ class ResidentLoader:
             yield [theta[s], x[s]]
 
 
+def _capture(body, stream):
+    """Capture ``body()`` (library launches only) into a CUDA graph.  Relaxed capture mode and a collected,
+    paused garbage collector: an unrelated object dying mid-capture (an old pipeline's pinned buffer, another
+    graph) would otherwise issue a CUDA call that invalidates the capture."""
+    import gc
+    gc.collect()
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream, capture_error_mode="relaxed"):
+            body()
+    finally:
+        if was:
+            gc.enable()
+    return graph
+
+
 class HostBatchPipeline:
     """Streams host batches through the fused step without ever idling the GPU on the host.
 
@@ -182,12 +200,7 @@ class HostBatchPipeline:
                 eng.pack(flat)
                 if self.peer:
                     parallel.reset_peer_epochs(eng)      # the step counter was rewound
-                self.graphs = []
-                for b in range(2):
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=self.comp_stream):
-                        self._body(b)
-                    self.graphs.append(g)
+                self.graphs = [_capture(lambda b=b: self._body(b), self.comp_stream) for b in range(2)]
             for b in range(2):
                 self.buf_free[b].record(self.comp_stream)
                 self.loss_read[b].record(self.comp_stream)
@@ -196,10 +209,13 @@ class HostBatchPipeline:
     def _body(self, b):
         eng, st = self.eng, self.t.state
         y = self.yd[b] if eng.n_cond else None
+        if not self.peer:
+            eng.train_step(self.flat, self.xd[b], y, self.loss_b[b], self.grad, st.opt_state["m"],
+                           st.opt_state["v"], st.step, st.tx, inv_global_b=self.inv, packed_current=True)
+            return
         eng.loss_grad(self.flat, self.xd[b], y, self.loss_b[b], self.grad, inv_global_b=self.inv,
-                      packed_current=True, dp_slot=self.peer)
-        if self.peer:
-            eng.dp_allreduce(self.grad, self.loss_b[b])
+                      packed_current=True, dp_slot=True)
+        eng.dp_allreduce(self.grad, self.loss_b[b])
         eng.clip_adam(self.flat, self.grad, st.opt_state["m"], st.opt_state["v"], st.step, st.tx,
                       norm_current=True)
 
@@ -445,6 +461,11 @@ class TrainerModule:
                               norm_current=True)
                 self._packed = True
                 return state, {"loss": loss[0].clone()}
+            if world == 1:
+                eng.train_step(flat, x, y, loss, grad, state.opt_state["m"], state.opt_state["v"], state.step,
+                               state.tx, packed_current=self._packed)
+                self._packed = True
+                return state, {"loss": loss[0].clone()}
             parallel.dp_step(
                 lambda g: eng.loss_grad(flat, x, y, loss, grad, inv_global_b=parallel.inv_global_batch(x.shape[0]),
                                         packed_current=self._packed),
@@ -488,10 +509,14 @@ class TrainerModule:
         inv = 1.0 / (batch_size * world)
 
         def body():
+            if not peer:
+                eng.train_step(flat, xd, yd, loss, grad, state.opt_state["m"], state.opt_state["v"], state.step,
+                               state.tx, batch_rows=batch_size, inv_global_b=inv, batch_index=state.step,
+                               n_batches=n_batches, packed_current=True)
+                return
             eng.loss_grad(flat, xd, yd, loss, grad, batch_rows=batch_size, inv_global_b=inv,
-                          batch_index=state.step, n_batches=n_batches, packed_current=True, dp_slot=peer)
-            if peer:
-                eng.dp_allreduce(grad, loss)       # own kernel over NVLink peer memory: graph-capturable
+                          batch_index=state.step, n_batches=n_batches, packed_current=True, dp_slot=True)
+            eng.dp_allreduce(grad, loss)       # own kernel over NVLink peer memory: graph-capturable
             eng.clip_adam(flat, grad, state.opt_state["m"], state.opt_state["v"], state.step, state.tx,
                           norm_current=True)
 
@@ -500,9 +525,7 @@ class TrainerModule:
         with torch.cuda.stream(s):
             body()                       # warm-up outside capture
             s.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=s):
-                body()
+            graph = _capture(body, s)
         torch.cuda.current_stream(eng.device).wait_stream(s)
         self._packed = True
         self._graph = graph

@@ -259,3 +259,35 @@ def test_hmc_trajectory_matches_restatement(name, act, n_steps):
     for key, ref in (("z", z1), ("p", p1), ("g", g1), ("theta", th1)):
         assert grad_err(S[key].cpu().numpy(), ref) < 2e-5, key
     assert rel_err(S["logdens"].cpu().numpy(), ld1) < 2e-5
+
+
+@pytest.mark.parametrize("kind", ["adam", "sgd", "adamw"])
+@pytest.mark.parametrize("name,B", [("c2", 4096), ("c1", 128), ("c3", 3001)])
+def test_train_step_equals_loss_grad_plus_clip_adam(name, B, kind):
+    """mafb200_train_step (flow kernel + one cooperative tail kernel) == loss_grad followed by clip_adam,
+    bit for bit: same reduction order, same update arithmetic."""
+    spec, flat, std, x, y = make_case(CONFIGS[name], B, seed=21)
+    hp = dict(lr=5e-3, warmup=0.1, decay_steps=50.0, clip=0.5)
+    outs = []
+    for fused in (False, True):
+        eng = _engine(spec, std)
+        opt = eng.make_opt_desc(kind=kind, weight_decay=1e-4 if kind != "adam" else 0.0, **hp)
+        p = _t(flat)
+        m, v, grad = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+        step = torch.zeros(1, dtype=torch.int32, device="cuda:0")
+        loss = torch.zeros(1, device="cuda:0")
+        xt, yt = _t(x), _t(y)
+        losses = []
+        for it in range(5):
+            if fused:
+                eng.train_step(p, xt, yt, loss, grad, m, v, step, opt, packed_current=it > 0)
+            else:
+                eng.loss_grad(p, xt, yt, loss, grad, packed_current=it > 0)
+                eng.clip_adam(p, grad, m, v, step, opt, norm_current=True)
+            losses.append(loss.item())
+        outs.append((losses, p.clone(), m.clone(), v.clone(), grad.clone(), int(step.item())))
+    a, b = outs
+    assert a[0] == b[0] and a[5] == b[5] == 5
+    for i in range(1, 5):
+        assert torch.equal(a[i], b[i]), i
+    assert b[0][-1] < b[0][0]
