@@ -17,6 +17,7 @@
  *                                jaxili/posterior/mcmc_posterior.py:139-159, 194-201
  *   mafb200_hmc_trajectory    <- numpyro HMC leapfrog integration inside MCMCPosterior.sample
  *                                jaxili/posterior/mcmc_posterior.py:78-118, 248-305
+ *   mafb200_pipeline_*        <- TrainerModule.train_epoch's host loop             jaxili/train.py:427-451
  *   mafb200_train_step        <- TrainerModule.create_functions().train_step    jaxili/train.py:330-335
  *   mafb200_clip_adam         <- state.apply_gradients(grads) with the optax chain built in
  *                                jaxili/train.py:246-300 (clip_by_global_norm -> adam(warmup_cosine))
@@ -230,6 +231,25 @@ int mafb200_train_step(mafb200_handle h, float* params, const float* x, const fl
                        float inv_global_B, const int32_t* batch_index, int64_t n_batches, float* out_loss,
                        float* out_grad, float* m, float* v, int32_t* step, const MafOptDesc* opt, int32_t flags,
                        void* stream);
+
+/* Host-batch pipeline: TrainerModule.train_epoch's loop over host batches (jaxili/train.py:427-451, which
+   relies on JAX's asynchronous dispatch and reads the loss once per epoch) as a native executor.  Batch i+1
+   is copied host->device on a copy stream while step i (one CUDA graph: mafb200_train_step, or loss_grad +
+   dp_allreduce + clip_adam with MAFB200_DP_SLOT) runs; every step's loss is copied device->host into a
+   pinned ring on a third stream.  params / m / v / step / grad are the caller's device buffers (as in
+   mafb200_train_step); after_stream orders the pipeline behind the caller's earlier work.
+   create runs one throw-away step on a saved copy of the optimiser state (restored before it returns);
+   capture builds the graphs; submit enqueues one step and returns; drain blocks until all submitted steps
+   are done and returns their losses. */
+typedef struct mafb200_pipeline_s* mafb200_pipeline;
+int mafb200_pipeline_create(mafb200_handle h, int64_t rows, float* params, float* m, float* v, int32_t* step,
+                            float* grad, const MafOptDesc* opt, float inv_global_B, int32_t flags,
+                            void* after_stream, mafb200_pipeline* out);
+int mafb200_pipeline_capture(mafb200_pipeline p);
+int mafb200_pipeline_fence(mafb200_pipeline p, void* after_stream);
+int mafb200_pipeline_submit(mafb200_pipeline p, const float* x, const float* y, int32_t pinned);
+int mafb200_pipeline_drain(mafb200_pipeline p, float* out_losses, int64_t cap, int64_t* n, float* last_loss_dev);
+int mafb200_pipeline_destroy(mafb200_pipeline p);
 
 /* optax.chain(clip_by_global_norm, adam(schedule)) + apply_gradients, in place on
    params / m / v; step[0] (device int32) is the optax count and is incremented.

@@ -87,6 +87,14 @@ SYMBOLS = {
     "mafb200_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.POINTER(MafOptDesc), C.c_int32, C.c_void_p]),
+    "mafb200_pipeline_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.POINTER(MafOptDesc), C.c_float, C.c_int32, C.c_void_p,
+                                          C.POINTER(C.c_void_p)]),
+    "mafb200_pipeline_capture": (C.c_int, [C.c_void_p]),
+    "mafb200_pipeline_fence": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mafb200_pipeline_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "mafb200_pipeline_drain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
+    "mafb200_pipeline_destroy": (C.c_int, [C.c_void_p]),
     "mafb200_clip_adam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.POINTER(MafOptDesc), C.c_int32, C.c_void_p]),
     "mafb200_sample_from_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -1328,6 +1328,8 @@ int mafb200_clip_adam(mafb200_handle h, float* params, const float* grad, float*
   return 0;
 }
 
+#include "pipeline.inc"
+
 static int sample_common(mafb200_handle h, const float* params, const float* u, uint64_t seed,
                          uint64_t row_offset, const float* y_obs, int64_t n_obs, int64_t rows_per_obs,
                          int64_t N, float* out, float* out_logdet, int32_t flags, void* stream) {

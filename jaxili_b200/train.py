@@ -122,8 +122,8 @@ class ResidentLoader:
 
 def _capture(body, stream):
     """Capture ``body()`` (library launches only) into a CUDA graph.  Relaxed capture mode and a collected,
-    paused garbage collector: an unrelated object dying mid-capture (an old pipeline's pinned buffer, another
-    graph) would otherwise issue a CUDA call that invalidates the capture."""
+    paused garbage collector: an unrelated object dying mid-capture (a pinned buffer, another graph) would
+    otherwise issue a CUDA call that invalidates the capture."""
     import gc
     gc.collect()
     was = gc.isenabled()
@@ -139,140 +139,99 @@ def _capture(body, stream):
 
 
 class HostBatchPipeline:
-    """Streams host batches through the fused step without ever idling the GPU on the host.
+    """Streams host batches through the fused step without ever idling the GPU on the host: a thin wrapper
+    over the native executor ``mafb200_pipeline_*`` (csrc/pipeline.inc).
 
     The reference's epoch loop hands numpy batches to a jitted step and relies on JAX's asynchronous
     dispatch, reading the loss once per epoch (jaxili/train.py:427-451).  The same contract here:
       * two device batch buffers; the H2D copy of batch i+1 runs on a copy stream while the compute stream
         executes step i (events order buffer reuse in both directions);
-      * the step (flow fwd+bwd, reduce, [peer all-reduce], clip+Adam) is one CUDA graph per buffer;
-      * every step's loss is copied D2H into a pinned ring right behind the step, on a third stream so the
-        4-byte copy's latency never sits between two steps (each graph owns its loss word); the host reads
-        the ring after ``drain()`` (one synchronisation per epoch, like ``.item()`` at train.py:449).
-    Batches that are pinned torch tensors are copied from where they lie; anything else goes through a ring
-    of pinned staging buffers whose reuse is guarded by the copy events (no host/DMA race)."""
-
-    N_STAGE = 4
+      * the step (flow fwd+bwd and the cooperative tail, or flow + reduce + peer all-reduce + clip/Adam under
+        torch.distributed) is one CUDA graph per buffer;
+      * every step's loss is copied D2H into a pinned ring on a third stream; the host reads the ring after
+        ``drain()`` (one synchronisation per epoch, like ``.item()`` at train.py:449).
+    Batches that are pinned torch tensors are copied from where they lie; anything else goes through the
+    executor's own pinned staging slots, whose reuse is guarded by the copy events."""
 
     def __init__(self, trainer, rows):
+        import ctypes as C
+        from . import _lib
         self.t, self.rows = trainer, rows
         eng = trainer.model.engine()
-        self.eng, dev = eng, eng.device
+        self.eng = eng
         state = trainer.state
         _, world = parallel.world_info()
         self.peer = world > 1 and parallel.setup_peer_allreduce(eng, state.step)
         if world > 1 and not self.peer:
             raise NotImplementedError("the streamed step under torch.distributed needs the peer-memory all-reduce")
-        self.use_graph = not eng.wide
-        f32 = dict(dtype=torch.float32, device=dev)
-        self.xd = [torch.zeros(rows, eng.n_in, **f32) for _ in range(2)]
-        self.yd = [torch.zeros(rows, max(eng.n_cond, 1), **f32) for _ in range(2)]
-        self.stage = [(torch.empty(rows, eng.n_in, dtype=torch.float32).pin_memory(),
-                       torch.empty(rows, max(eng.n_cond, 1), dtype=torch.float32).pin_memory())
-                      for _ in range(self.N_STAGE)]
-        self.stage_free = [None] * self.N_STAGE
-        self.copy_stream, self.comp_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        self.d2h_stream = torch.cuda.Stream(device=dev)
-        self.h2d_done = [torch.cuda.Event() for _ in range(2)]
-        self.buf_free = [torch.cuda.Event() for _ in range(2)]
-        self.loss_read = [torch.cuda.Event() for _ in range(2)]
-        self.loss_b = [torch.zeros(1, **f32) for _ in range(2)]
-        self.ring = torch.zeros(4096, dtype=torch.float32).pin_memory()
-        self.i = self.base = 0
         flat = state.params.flat
         P = flat.numel()
         self.flat, self.grad = flat, trainer._gbuf[:P]
-        self.inv = 1.0 / (rows * world)
-        cur = torch.cuda.current_stream(dev)
-        self.comp_stream.wait_stream(cur)
-        self.copy_stream.wait_stream(cur)
-        with torch.cuda.stream(self.comp_stream):
-            eng.pack(flat)
-            if self.use_graph:
-                # one throw-away launch outside capture (lazy module load), on a copy of the optimiser state
-                keep = [t.clone() for t in (flat, state.opt_state["m"], state.opt_state["v"], state.step)
-                        if t is not None]
-                self._body(0)
-                self.comp_stream.synchronize()
-                for t, k in zip([t for t in (flat, state.opt_state["m"], state.opt_state["v"], state.step)
-                                 if t is not None], keep):
-                    t.copy_(k)
-                eng.pack(flat)
-                if self.peer:
-                    parallel.reset_peer_epochs(eng)      # the step counter was rewound
-                self.graphs = [_capture(lambda b=b: self._body(b), self.comp_stream) for b in range(2)]
-            for b in range(2):
-                self.buf_free[b].record(self.comp_stream)
-                self.loss_read[b].record(self.comp_stream)
+        self._keep = (flat, state.opt_state["m"], state.opt_state["v"], state.step, trainer._gbuf, state.tx)
+        self.lib, self._C, self._check = eng.lib, C, _lib.check
+        h = C.c_void_p()
+        cur = torch.cuda.current_stream(eng.device).cuda_stream
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        self._check(self.lib.mafb200_pipeline_create(
+            eng._h, rows, ptr(flat), ptr(state.opt_state["m"]), ptr(state.opt_state["v"]), ptr(state.step),
+            ptr(self.grad), C.byref(state.tx), 1.0 / (rows * world), _lib.DP_SLOT if self.peer else 0,
+            C.c_void_p(cur), C.byref(h)))
+        self._p = h
+        if self.peer:
+            parallel.reset_peer_epochs(eng)          # create's throw-away step advanced, then rewound, the count
+        self._check(self.lib.mafb200_pipeline_capture(self._p))
+        self.i = self.base = 0
+        self._out = np.empty(8192, np.float32)
         trainer._packed = True
 
-    def _body(self, b):
-        eng, st = self.eng, self.t.state
-        y = self.yd[b] if eng.n_cond else None
-        if not self.peer:
-            eng.train_step(self.flat, self.xd[b], y, self.loss_b[b], self.grad, st.opt_state["m"],
-                           st.opt_state["v"], st.step, st.tx, inv_global_b=self.inv, packed_current=True)
-            return
-        eng.loss_grad(self.flat, self.xd[b], y, self.loss_b[b], self.grad, inv_global_b=self.inv,
-                      packed_current=True, dp_slot=True)
-        eng.dp_allreduce(self.grad, self.loss_b[b])
-        eng.clip_adam(self.flat, self.grad, st.opt_state["m"], st.opt_state["v"], st.step, st.tx,
-                      norm_current=True)
+    def __del__(self):
+        p, self._p = getattr(self, "_p", None), None
+        if p:
+            try:
+                self.lib.mafb200_pipeline_destroy(p)
+            except Exception:
+                pass
 
-    def _source(self, a, which):
-        """A pinned host view of ``a`` [rows, cols]: the tensor itself if it already is pinned, else a staging copy."""
-        if isinstance(a, torch.Tensor) and a.dtype == torch.float32 and a.is_pinned() and a.is_contiguous():
-            return a.reshape(self.rows, -1), None
-        k = self.i % self.N_STAGE
-        if which == 0 and self.stage_free[k] is not None:
-            self.stage_free[k].synchronize()          # the DMA that last read this staging slot has finished
-        dst = self.stage[k][which]
-        src = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float32)
-        dst.numpy()[...] = src.reshape(dst.shape)
-        return dst, k
+    def fence(self):
+        """Order the pipeline behind everything enqueued on torch's current stream."""
+        cur = torch.cuda.current_stream(self.eng.device).cuda_stream
+        self._check(self.lib.mafb200_pipeline_fence(self._p, self._C.c_void_p(cur)))
+
+    def _host(self, a, cols):
+        """(pointer, pinned?, keep-alive) of a host batch [rows, cols]."""
+        if isinstance(a, torch.Tensor):
+            if a.dtype != torch.float32 or not a.is_contiguous():
+                a = a.to(torch.float32).contiguous()
+            if a.numel() != self.rows * cols:
+                raise ValueError(f"batch has {a.numel()} values, the pipeline expects {self.rows} x {cols}")
+            return a.data_ptr(), a.is_pinned(), a
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        if a.size != self.rows * cols:
+            raise ValueError(f"batch has {a.size} values, the pipeline expects {self.rows} x {cols}")
+        return a.ctypes.data, False, a
 
     def submit(self, batch):
         xb, yb = self.t._batch_xy(batch)
-        b = self.i & 1
-        sx, kx = self._source(xb, 0)
-        sy, ky = self._source(yb, 1) if self.eng.n_cond else (None, None)
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(self.buf_free[b])       # step i-2 no longer reads this device buffer
-            self.xd[b].copy_(sx, non_blocking=True)
-            if sy is not None:
-                self.yd[b].copy_(sy, non_blocking=True)
-            self.h2d_done[b].record(self.copy_stream)
-        if kx is not None or ky is not None:
-            k = kx if kx is not None else ky
-            if self.stage_free[k] is None:
-                self.stage_free[k] = torch.cuda.Event()
-            self.stage_free[k].record(self.copy_stream)
-        slot = self.i - self.base
-        if slot >= self.ring.numel():
-            raise RuntimeError("loss ring full: call drain() at least every 4096 steps")
-        with torch.cuda.stream(self.comp_stream):
-            self.comp_stream.wait_event(self.h2d_done[b])
-            self.comp_stream.wait_event(self.loss_read[b])      # step i-2's loss word has been copied out
-            if self.use_graph:
-                self.graphs[b].replay()
-            else:
-                self._body(b)
-            self.buf_free[b].record(self.comp_stream)
-        with torch.cuda.stream(self.d2h_stream):
-            self.d2h_stream.wait_event(self.buf_free[b])
-            self.ring[slot:slot + 1].copy_(self.loss_b[b], non_blocking=True)   # D2H read of this step's loss
-            self.loss_read[b].record(self.d2h_stream)
+        px, pin_x, kx = self._host(xb, self.eng.n_in)
+        if self.eng.n_cond:
+            py, pin_y, ky = self._host(yb, self.eng.n_cond)
+        else:
+            py, pin_y, ky = None, True, None
+        if self.i - self.base >= 8192:
+            raise RuntimeError("loss ring full: call drain() at least every 8192 steps")
+        self._check(self.lib.mafb200_pipeline_submit(self._p, self._C.c_void_p(px),
+                                                     self._C.c_void_p(py) if py else None,
+                                                     1 if (pin_x and pin_y) else 0))
         self.i += 1
 
     def drain(self):
         """Wait for everything submitted; returns the per-step losses since the previous drain (numpy)."""
-        self.comp_stream.synchronize()
-        self.d2h_stream.synchronize()
-        out = self.ring[: self.i - self.base].numpy().copy()
+        n = self._C.c_int64()
+        self._check(self.lib.mafb200_pipeline_drain(
+            self._p, self._C.c_void_p(self._out.ctypes.data), self._out.size, self._C.byref(n),
+            self._C.c_void_p(self.t._gbuf[-4:-3].data_ptr())))     # where the plain step leaves its loss
         self.base = self.i
-        torch.cuda.current_stream(self.eng.device).wait_stream(self.comp_stream)
-        self.t._gbuf[-4:-3].copy_(self.loss_b[(self.i - 1) & 1])      # where the plain step leaves its loss
-        return out
+        return self._out[: n.value].copy()
 
 
 class TrainerModule:
@@ -622,6 +581,7 @@ class TrainerModule:
                 # device-resident batches need no staging: plain step
                 if pipe is not None:
                     total += float(pipe.drain().sum())
+                    pipe = None                      # re-fenced behind the plain step when used again
                 self.state, m = self.train_step(self.state, batch)
                 total += float(m["loss"].item())
                 n += 1
@@ -630,7 +590,8 @@ class TrainerModule:
                 if pipe is not None:
                     total += float(pipe.drain().sum())
                 pipe = self.host_pipeline(rows)
-            if pipe.i - pipe.base >= pipe.ring.numel():
+                pipe.fence()
+            if pipe.i - pipe.base >= 8192:
                 total += float(pipe.drain().sum())
             pipe.submit(batch)
             n += 1

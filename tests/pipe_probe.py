@@ -23,7 +23,6 @@ tr.init_optimizer(100, 1000)
 hb = [[torch.from_numpy(theta[i * rows:(i + 1) * rows]).pin_memory(), torch.from_numpy(x[i * rows:(i + 1) * rows]).pin_memory()] for i in range(16)]
 pipe = tr.host_pipeline(rows)
 N = 1000
-# the real thing
 for i in range(50):
     pipe.submit(hb[i % 16])
 pipe.drain()
@@ -34,3 +33,11 @@ t1 = time.perf_counter()
 pipe.drain()
 t2 = time.perf_counter()
 print(f"pipe.submit host {1e6 * (t1 - t0) / N:6.1f} us/submit   total {1e6 * (t2 - t0) / N:6.1f} us/step")
+for n in (300, 300, 1000, 3000):
+    loader = [hb[i % 16] for i in range(n)]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tr.train_epoch(loader)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    print(f"train_epoch {n} steps: {1e6 * (t1 - t0) / n:6.1f} us/step")
