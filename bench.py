@@ -468,7 +468,8 @@ def main():
                                   batch_index=state.step, n_batches=n_batches, packed_current=True)
                     dist.all_reduce(gbuf)
                     eng.clip_adam(flat, grad, state.opt_state["m"], state.opt_state["v"], state.step, state.tx)
-            launches_per_step = 4          # flow, reduce, all-reduce (own kernel or sqnorm + NCCL's), clip_adam
+            # peer: flow kernel + cooperative tail (reduce, exchange, clip, Adam); NCCL: flow, reduce, NCCL's, clip_adam
+            launches_per_step = 2 if peer else 4
         for _ in range(W):
             step_fn()
         barrier_sync()

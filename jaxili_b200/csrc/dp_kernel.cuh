@@ -93,4 +93,173 @@ __global__ void __launch_bounds__(RED_IDX) dp_allreduce_kernel(const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Whole tail of a training step in ONE launch: reduction of the per-CTA partial gradients (reduce_kernel),
+// [DP: one-shot exchange with the peers, as dp_allreduce_kernel], global norm, clip + schedule + Adam +
+// re-pack of the weight images (clip_adam_kernel).  The global norm needs every block's partial, so the
+// blocks meet at a grid barrier (two with DP: the rank's slot must be complete before its epoch flag is
+// raised); the kernel is launched cooperatively (all ceil(P/256) blocks co-resident: narrow models only)
+// and each parameter's gradient stays in the register of the thread that produced it across the barriers.
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, bool system_scope) {
+  // monotone 64-bit ticket counter (never reset, no wrap); one thread per block calls this after a
+  // __syncthreads(), which makes the block's earlier writes cumulative with its fence
+  if (system_scope) __threadfence_system();
+  else __threadfence();
+  const unsigned long long ticket = atomicAdd(bar, 1ull);
+  const unsigned long long target = (ticket / gridDim.x + 1ull) * gridDim.x;
+  unsigned long long seen;
+  do {
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(bar) : "memory");
+  } while (seen < target);
+}
+
+template <bool DP>
+__global__ void __launch_bounds__(RED_IDX * RED_PARTS)
+step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs O, const float* __restrict__ partial,
+                 int G, const unsigned char* __restrict__ mask, float* __restrict__ grad,
+                 const float* __restrict__ partial_loss, float* __restrict__ loss, float* __restrict__ normpart,
+                 float* __restrict__ params, float* __restrict__ m, float* __restrict__ v, int* __restrict__ step,
+                 float* __restrict__ wimg, unsigned long long* __restrict__ grid_bar,
+                 const __grid_constant__ DpArgs a) {
+  __shared__ float red[RED_PARTS][RED_IDX];
+  __shared__ float wsum[RED_IDX / 32];
+  __shared__ float lsum[RED_IDX / 32];
+  __shared__ float s_norm;
+  __shared__ int s_ok;
+  const int i = threadIdx.x % RED_IDX, p = threadIdx.x / RED_IDX;
+  const int idx = blockIdx.x * RED_IDX + i;
+  const int t = step[0];
+  // DP: the locally reduced gradient goes to this rank's symmetric slot of the coming epoch (= count + 1)
+  const unsigned int epoch = (unsigned int)t + 1u;
+  const long long soff = DP ? (long long)(epoch & 1u) * a.slot_floats : 0;
+  float* own = DP ? const_cast<float*>(a.sym[a.rank]) + soff : nullptr;
+  float s = 0.f;
+  if (idx < P.P) {
+    const float* src = partial + idx;
+#pragma unroll 4
+    for (int g = p; g < G; g += RED_PARTS) s += src[(size_t)g * P.P];
+  }
+  red[p][i] = s;
+  // operands of the update, fetched while the partial sums are in flight
+  float pv = 0.f, mv = 0.f, vv = 0.f;
+  unsigned char mk = 0;
+  if (p == 0 && idx < P.P) {
+    pv = params[idx];
+    mk = mask[idx];
+    if (O.kind != 1) { mv = m[idx]; vv = v[idx]; }
+  }
+  __syncthreads();
+  float g = 0.f;
+  if (p == 0) {
+    if (idx < P.P) {
+      g = ((red[0][i] + red[1][i]) + (red[2][i] + red[3][i]));
+      g = mk ? g : 0.f;
+      if (DP) own[idx] = g;
+      else grad[idx] = g;
+    }
+    if (!DP) {
+      const float sq = warp_sum(g * g);
+      if ((i & 31) == 0) wsum[i >> 5] = sq;
+    }
+  } else if (blockIdx.x == 0 && p == 1) {   // second part-group of block 0 reduces the loss
+    float l = 0.f;
+    for (int q = i; q < G; q += RED_IDX) l += partial_loss[q];
+    l = warp_sum(l);
+    if ((i & 31) == 0) lsum[i >> 5] = l;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (!DP) {
+      float tt = 0.f;
+      for (int w = 0; w < RED_IDX / 32; ++w) tt += wsum[w];
+      normpart[blockIdx.x] = tt;
+    }
+    if (blockIdx.x == 0) {
+      float l = 0.f;
+      for (int w = 0; w < RED_IDX / 32; ++w) l += lsum[w];
+      if (DP) own[(P.P + 3) & ~3] = l;
+      else loss[0] = l;
+    }
+    s_ok = 1;
+    grid_barrier(grid_bar, DP);
+  }
+  __syncthreads();
+  if (p != 0) return;
+  if (DP) {
+    // the whole slot of this rank is written and fenced: raise the epoch flag in every peer, wait for theirs
+    if (blockIdx.x == 0 && i < a.world) st_release_sys(a.flags_of[i] + a.rank, epoch);
+    if (i < a.world) {
+      const unsigned int* f = a.flags_of[a.rank] + i;
+      const long long t0 = clock64();
+      while ((int)(ld_acquire_sys(f) - epoch) < 0) {       // epochs only grow; signed difference tolerates wrap
+        if (clock64() - t0 > a.timeout_cycles) {
+          s_ok = 0;
+          *a.error = 1u;
+          break;
+        }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(RED_IDX));
+    g = 0.f;
+    if (s_ok && idx < P.P) {
+#pragma unroll
+      for (int r = 0; r < DP_MAX_WORLD; ++r)
+        if (r < a.world) g += a.sym[r][soff + idx];           // fixed order: replicas stay bit-identical
+      grad[idx] = g;
+    }
+    const float sq = warp_sum(g * g);
+    if ((i & 31) == 0) wsum[i >> 5] = sq;
+    asm volatile("bar.sync 1, %0;" ::"n"(RED_IDX));
+    if (i == 0) {
+      float tt = 0.f;
+      for (int w = 0; w < RED_IDX / 32; ++w) tt += wsum[w];
+      normpart[blockIdx.x] = tt;
+      if (blockIdx.x == 0) {
+        const int lo = (P.P + 3) & ~3;
+        float l = 0.f;
+        for (int r = 0; r < a.world; ++r) l += a.sym[r][soff + lo];
+        loss[0] = s_ok ? l : __int_as_float(0x7fc00000);
+      }
+      grid_barrier(grid_bar, false);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(RED_IDX));
+  }
+  // every block sums the norm partials in the same fixed order -> identical scale everywhere
+  float ns = 0.f;
+  for (int q = i; q < (int)gridDim.x; q += RED_IDX) ns += __ldcg(normpart + q);
+  ns = warp_sum(ns);
+  if ((i & 31) == 0) wsum[i >> 5] = ns;
+  asm volatile("bar.sync 1, %0;" ::"n"(RED_IDX));
+  if (i == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < RED_IDX / 32; ++w) tot += wsum[w];
+    s_norm = sqrtf(tot);
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(RED_IDX));
+  const float gnorm = s_norm;
+  if (idx < P.P) {
+    if (!(gnorm < O.clip)) g = (g / gnorm) * O.clip;
+    const float lr_t = lr_schedule(O, t);
+    float upd;
+    if (O.kind == 1) {
+      upd = g + O.weight_decay * pv;
+    } else {
+      const float mm = O.b1 * mv + (1.f - O.b1) * g;
+      const float v2 = O.b2 * vv + (1.f - O.b2) * g * g;
+      m[idx] = mm;
+      v[idx] = v2;
+      const float tn = (float)(t + 1);
+      const float mhat = mm / (1.f - powf(O.b1, tn));
+      const float vhat = v2 / (1.f - powf(O.b2, tn));
+      upd = mhat / (sqrtf(vhat) + O.eps);
+      if (O.kind == 2) upd += O.weight_decay * pv;
+    }
+    pv = pv - lr_t * upd;
+    params[idx] = pv;
+    write_image(P, wimg, idx, mk ? pv : 0.f);
+  }
+  // every block read step[0] before the barrier
+  if (blockIdx.x == 0 && i == 0) step[0] = t + 1;
+}
+
 }  // namespace mafb

@@ -1251,16 +1251,29 @@ int mafb200_train_step(mafb200_handle h, float* params, const float* x, const fl
                        void* stream) {
   if (!h || !params || !x || (h->desc.n_cond && !y) || !out_loss || !out_grad || !step || !opt)
     return fail("null argument");
-  if (flags & MAFB200_DP_SLOT) return fail("train_step is the single-rank step; use loss_grad + dp_allreduce + clip_adam");
+  const bool dp = (flags & MAFB200_DP_SLOT) != 0;
+  if (dp) {
+    if (!h->dp_sym || !h->dp_step) return fail("MAFB200_DP_SLOT needs mafb200_dp_init and mafb200_dp_bind_step");
+    if (h->dp_step != step) return fail("MAFB200_DP_SLOT: step must be the counter bound with mafb200_dp_bind_step");
+    if (h->wide) return fail("the peer-memory all-reduce serves the fused narrow path; use NCCL for wide models");
+    for (int r = 0; r < h->dp_world; ++r)
+      if (!h->dp_peer_sym[r]) return fail("dp peers not connected");
+  }
   if (opt->kind < 0 || opt->kind > 2) return fail("unknown optimizer kind");
   if (opt->kind != 1 && (!m || !v)) return fail("adam needs m and v");
   if (opt->decay_steps - opt->warmup <= 0.f) return fail("cosine_decay_schedule requires positive decay_steps");
   if (!h->wide && h->tail_ok < 0) {
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_tail_kernel, RED_IDX * RED_PARTS, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_tail_kernel<true>, RED_IDX * RED_PARTS, 0));
     int coop = 0;
     CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
     h->tail_ok = (coop && (long long)per_sm * h->n_sm >= h->n_norm) ? 1 : 0;
+  }
+  if (dp && h->tail_ok != 1) {
+    if (mafb200_loss_grad(h, params, x, y, B, inv_global_B, batch_index, n_batches, nullptr, nullptr, flags, stream))
+      return 1;
+    if (mafb200_dp_allreduce(h, out_grad, out_loss, stream)) return 1;
+    return mafb200_clip_adam(h, params, out_grad, m, v, step, opt, MAFB200_NORM_CURRENT, stream);
   }
   if (h->wide || h->tail_ok != 1) {
     if (mafb200_loss_grad(h, params, x, y, B, inv_global_B, batch_index, n_batches, out_loss, out_grad, flags, stream))
@@ -1301,9 +1314,25 @@ int mafb200_train_step(mafb200_handle h, float* params, const float* x, const fl
   float* normpart = h->normpart;
   float* wimg = h->wimg;
   unsigned long long* bar = h->grid_bar;
+  DpArgs a{};
+  if (dp) {
+    a.rank = h->dp_rank;
+    a.world = h->dp_world;
+    a.P = Pk.P;
+    a.step = h->dp_step;
+    const size_t sf = dp_slot_floats(Pk);
+    a.slot_floats = (long long)sf;
+    for (int r = 0; r < h->dp_world; ++r) {
+      a.sym[r] = h->dp_peer_sym[r];
+      a.flags_of[r] = reinterpret_cast<unsigned int*>(h->dp_peer_sym[r] + 2 * sf);
+    }
+    a.error = h->dp_error;
+    a.timeout_cycles = 4000000000LL;
+  }
   void* args[] = {&Pk, &O, &partial, &grid, &mask, &out_grad, &ploss, &out_loss, &normpart, &params,
-                  &m, &v, &step, &wimg, &bar};
-  CU(cudaLaunchCooperativeKernel((const void*)step_tail_kernel, dim3(h->n_norm), dim3(RED_IDX * RED_PARTS), args, 0, st));
+                  &m, &v, &step, &wimg, &bar, &a};
+  const void* fn = dp ? (const void*)step_tail_kernel<true> : (const void*)step_tail_kernel<false>;
+  CU(cudaLaunchCooperativeKernel(fn, dim3(h->n_norm), dim3(RED_IDX * RED_PARTS), args, 0, st));
   return 0;
 }
 

@@ -265,8 +265,10 @@ class MafEngine:
         return o
 
     def train_step(self, params, x, y, out_loss, out_grad, m, v, step, opt, batch_rows=None, inv_global_b=None,
-                   batch_index=None, n_batches=1, packed_current=False):
-        """loss_grad + clip_adam as one call (single rank): flow kernel + one cooperative tail kernel."""
+                   batch_index=None, n_batches=1, packed_current=False, dp_slot=False):
+        """loss_grad [+ peer all-reduce] + clip_adam as one call: flow kernel + one cooperative tail kernel.
+        ``dp_slot=True``: data parallel over NVLink peer memory (``dp_init`` / ``dp_connect`` / ``dp_bind_step``
+        done, ``inv_global_b`` = 1 / global batch); the exchange happens inside the tail kernel."""
         if step.dtype != torch.int32 or not step.is_cuda:
             raise TypeError("step must be an int32 CUDA tensor")
         px = self._chk(x, "x", self.n_in)
@@ -283,8 +285,8 @@ class MafEngine:
             self._h, self._chk(params, "params"), px, py, B, inv, bi, int(n_batches),
             self._chk(out_loss, "out_loss"), self._chk(out_grad, "out_grad"),
             self._chk(m, "m") if m is not None else None, self._chk(v, "v") if v is not None else None,
-            C.c_void_p(step.data_ptr()), C.byref(opt), _lib.PACKED_CURRENT if packed_current else 0,
-            self._stream()))
+            C.c_void_p(step.data_ptr()), C.byref(opt),
+            (_lib.PACKED_CURRENT if packed_current else 0) | (_lib.DP_SLOT if dp_slot else 0), self._stream()))
 
     def clip_adam(self, params, grad, m, v, step, opt, norm_current=False):
         """In-place optax-chain update; ``step`` is an int32 CUDA tensor (the optax count)."""

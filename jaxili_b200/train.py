@@ -413,11 +413,9 @@ class TrainerModule:
             if world > 1 and parallel.setup_peer_allreduce(eng, state.step):
                 # latency-bound gradient (<= 1 MB): one-shot all-reduce over NVLink peer memory, fused
                 # with the norm partials; replicas stay bit-identical (fixed rank order)
-                eng.loss_grad(flat, x, y, loss, grad, inv_global_b=parallel.inv_global_batch(x.shape[0]),
-                              packed_current=self._packed, dp_slot=True)
-                eng.dp_allreduce(grad, loss)
-                eng.clip_adam(flat, grad, state.opt_state["m"], state.opt_state["v"], state.step, state.tx,
-                              norm_current=True)
+                eng.train_step(flat, x, y, loss, grad, state.opt_state["m"], state.opt_state["v"], state.step,
+                               state.tx, inv_global_b=parallel.inv_global_batch(x.shape[0]),
+                               packed_current=self._packed, dp_slot=True)
                 self._packed = True
                 return state, {"loss": loss[0].clone()}
             if world == 1:
@@ -468,16 +466,11 @@ class TrainerModule:
         inv = 1.0 / (batch_size * world)
 
         def body():
-            if not peer:
-                eng.train_step(flat, xd, yd, loss, grad, state.opt_state["m"], state.opt_state["v"], state.step,
-                               state.tx, batch_rows=batch_size, inv_global_b=inv, batch_index=state.step,
-                               n_batches=n_batches, packed_current=True)
-                return
-            eng.loss_grad(flat, xd, yd, loss, grad, batch_rows=batch_size, inv_global_b=inv,
-                          batch_index=state.step, n_batches=n_batches, packed_current=True, dp_slot=True)
-            eng.dp_allreduce(grad, loss)       # own kernel over NVLink peer memory: graph-capturable
-            eng.clip_adam(flat, grad, state.opt_state["m"], state.opt_state["v"], state.step, state.tx,
-                          norm_current=True)
+            # flow kernel + one cooperative tail kernel; with peers the one-shot exchange over NVLink peer
+            # memory happens inside the tail (own kernel, graph-capturable -- unlike the NCCL call)
+            eng.train_step(flat, xd, yd, loss, grad, state.opt_state["m"], state.opt_state["v"], state.step,
+                           state.tx, batch_rows=batch_size, inv_global_b=inv, batch_index=state.step,
+                           n_batches=n_batches, packed_current=True, dp_slot=peer)
 
         s = torch.cuda.Stream(device=eng.device)
         s.wait_stream(torch.cuda.current_stream(eng.device))

@@ -36,11 +36,35 @@ for i in range(4):
     l_ref, g_ref = onp.nll_loss_and_grad(spec, ref, std, theta[gb].astype(np.float64), x[gb].astype(np.float64))
     assert abs(m["loss"].item() - l_ref) < 2e-5 * max(1, abs(l_ref)), (m["loss"].item(), l_ref)
     ref, _, _ = onp.clip_adam_step(ref, g_ref, st, 1e-3, 0.1, float(int(100 // 2 * 4)), clip=0.05)
+# the streamed epoch (native pipeline, fused tail with the peer exchange inside) continues the same trajectory
+lo, hi = parallel.shard_rows(B, rank, world)
+loader = [[theta[i * B:(i + 1) * B][lo:hi], x[i * B:(i + 1) * B][lo:hi]] for i in range(4)]
+# FP32 envelope: the same restatement run in float32 from the current state (oracle (2))
+ref32 = ref.astype(np.float32)
+st32 = onp.AdamState(ref.size, np.float32)
+st32.m, st32.v, st32.count = st.m.astype(np.float32), st.v.astype(np.float32), st.count
+for ep in range(2):
+    met = tr.train_epoch(loader)
+    l_mean = 0.0
+    for i in range(4):
+        gb = slice(i * B, (i + 1) * B)
+        l_ref, g_ref = onp.nll_loss_and_grad(spec, ref, std, theta[gb].astype(np.float64), x[gb].astype(np.float64))
+        l_mean += l_ref / 4
+        _, g32 = onp.nll_loss_and_grad(spec, ref32, std, theta[gb], x[gb])
+        ref32, _, _ = onp.clip_adam_step(ref32, g32.astype(np.float32), st32, 1e-3, 0.1, float(int(100 // 2 * 4)), clip=0.05)
+        ref, _, _ = onp.clip_adam_step(ref, g_ref, st, 1e-3, 0.1, float(int(100 // 2 * 4)), clip=0.05)
+    assert abs(met["train/loss"] - l_mean) < 2e-5 * max(1, abs(l_mean)), (met["train/loss"], l_mean)
+streamed = tr._pipeline is not None
 flat = tr.state.params.flat
-assert np.max(np.abs(flat.cpu().numpy() - ref)) < 5e-6
+assert int(tr.state.step.item()) == 12
+dev = np.abs(flat.cpu().numpy() - ref)
+# Adam normalises by sqrt(v): entries whose gradient is at FP32 noise level take lr-sized steps of either sign, so
+# over 12 steps the bound is the FP32 envelope (float32 restatement vs float64 restatement), not a constant
+env = np.abs(ref32.astype(np.float64) - ref)
+assert dev.max() < 5e-3 and np.quantile(dev, 0.99) < 5e-6 + 3 * np.quantile(env, 0.99), (dev.max(), np.quantile(dev, 0.99), np.quantile(env, 0.99), env.max())
 gathered = [torch.empty_like(flat) for _ in range(world)]
 dist.all_gather(gathered, flat)
 assert all(torch.equal(g, gathered[0]) for g in gathered), "replicas diverged"
 if rank == 0:
-    print(f"dp_check ok: world={world}, replicas bit-identical, max |p - oracle| = {np.max(np.abs(flat.cpu().numpy() - ref)):.2e}")
+    print(f"dp_check ok: world={world}, streamed_epoch={streamed}, peer_error={tr.model.engine().dp_error() if world > 1 and streamed else None}, replicas bit-identical, max |p - oracle| = {np.max(np.abs(flat.cpu().numpy() - ref)):.2e}")
 dist.destroy_process_group()
