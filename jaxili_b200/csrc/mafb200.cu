@@ -445,7 +445,9 @@ int wide_launch_tc(const GemmArgs& g, bool relu, int splits, cudaStream_t st) {
       kfn<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, g);                                         \
     }                                                                                                      \
   } while (0)
-  if (g.N >= 256 && g.M >= 256) WTC(256, 256);
+  static const int tile_mode = [] { const char* e = getenv("MAFB200_TC_TILE"); return e ? atoi(e) : 0; }();
+  if (g.N >= 256 && g.M >= 256 && tile_mode == 1) WTC(128, 256);
+  else if (g.N >= 256 && g.M >= 256) WTC(256, 256);
   else if (g.N > 64) WTC(128, 128);
   else if (g.N > 32) WTC(128, 64);
   else WTC(128, 32);

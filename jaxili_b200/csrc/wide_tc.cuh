@@ -91,7 +91,9 @@ __host__ __device__ constexpr uint32_t tc_instr_desc(int M, int N, bool a_mn, bo
 template <int BM, int BN>
 struct TcCfg {
   static constexpr int MH = BM / 128;                   // 128-row halves, one MMA + accumulator each
-  static constexpr int STAGES = (BM * BN >= 256 * 256) ? 3 : (BN >= 128 ? 3 : 4);
+  // 128x256: two stages (97 KB) so that TWO CTAs share an SM (256 TMEM columns each): one CTA's epilogue
+  // (TMEM -> registers -> shared -> global) overlaps the other's TMA/MMA main loop
+  static constexpr int STAGES = (BM == 128 && BN == 256) ? 2 : ((BM * BN >= 256 * 256) ? 3 : (BN >= 128 ? 3 : 4));
   static constexpr int A_BYTES = BM * TC_BK * 4;        // 16 KB per half
   static constexpr int B_BYTES = BN * TC_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
