@@ -32,12 +32,21 @@ struct DpArgs {
   float* normpart;                        // local [ceil(P / RED_IDX)]
   unsigned int* error;                    // local: set to 1 on time-out
   long long timeout_cycles;
+  long long* trace;                       // debug (nullable): %globaltimer stamps of block 0 in step_tail_kernel
+  // push protocol of step_tail_kernel<true>: every rank owns a receive area [2 parities][DP_MAX_WORLD sources]
+  // [slot_floats] at float offset recv_off of its symmetric buffer and per-(source, block) epoch flags at
+  // float offset flagsb_off ([DP_MAX_WORLD][n_blocks] u32)
+  long long recv_off, flagsb_off;
+  int n_blocks;
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -128,11 +137,19 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
   __shared__ int s_ok;
   const int i = threadIdx.x % RED_IDX, p = threadIdx.x / RED_IDX;
   const int idx = blockIdx.x * RED_IDX + i;
+  auto tstamp = [&](int k) {
+    if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      a.trace[k] = (long long)now;
+    }
+  };
+  tstamp(0);
   const int t = step[0];
-  // DP: the locally reduced gradient goes to this rank's symmetric slot of the coming epoch (= count + 1)
+  // DP: the locally reduced gradient is PUSHED into every rank's receive area of the coming epoch
+  // (= count + 1; parity alternates): remote stores are fire-and-forget, the later sum reads local memory only
   const unsigned int epoch = (unsigned int)t + 1u;
-  const long long soff = DP ? (long long)(epoch & 1u) * a.slot_floats : 0;
-  float* own = DP ? const_cast<float*>(a.sym[a.rank]) + soff : nullptr;
+  const long long roff = DP ? a.recv_off + ((long long)(epoch & 1u) * DP_MAX_WORLD + a.rank) * a.slot_floats : 0;
   float s = 0.f;
   if (idx < P.P) {
     const float* src = partial + idx;
@@ -154,8 +171,13 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
     if (idx < P.P) {
       g = ((red[0][i] + red[1][i]) + (red[2][i] + red[3][i]));
       g = mk ? g : 0.f;
-      if (DP) own[idx] = g;
-      else grad[idx] = g;
+      if (DP) {
+#pragma unroll
+        for (int r = 0; r < DP_MAX_WORLD; ++r)
+          if (r < a.world) const_cast<float*>(a.sym[r])[roff + idx] = g;
+      } else {
+        grad[idx] = g;
+      }
     }
     if (!DP) {
       const float sq = warp_sum(g * g);
@@ -177,19 +199,35 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
     if (blockIdx.x == 0) {
       float l = 0.f;
       for (int w = 0; w < RED_IDX / 32; ++w) l += lsum[w];
-      if (DP) own[(P.P + 3) & ~3] = l;
-      else loss[0] = l;
+      if (DP) {
+        for (int r = 0; r < a.world; ++r) const_cast<float*>(a.sym[r])[roff + ((P.P + 3) & ~3)] = l;
+      } else {
+        loss[0] = l;
+      }
     }
     s_ok = 1;
-    grid_barrier(grid_bar, DP);
+    tstamp(1);
+    if (!DP) grid_barrier(grid_bar, false);
   }
+  if (DP && threadIdx.x < a.world) {
+    // this block's 256 entries are on their way to every rank: ONE system-scope fence for the warp (cumulative
+    // over the block's stores, which the __syncthreads above ordered before these lanes), then lane r raises
+    // the block's epoch flag on rank r with a relaxed store -- a release store per flag would repeat the fence
+    // and serialise one NVLink round trip per peer.  No grid barrier: block b only needs the peers' block b.
+    __threadfence_system();
+    st_relaxed_sys(reinterpret_cast<unsigned int*>(const_cast<float*>(a.sym[threadIdx.x]) + a.flagsb_off) +
+                       (long long)a.rank * a.n_blocks + blockIdx.x,
+                   epoch);
+  }
+  tstamp(2);
   __syncthreads();
   if (p != 0) return;
   if (DP) {
-    // the whole slot of this rank is written and fenced: raise the epoch flag in every peer, wait for theirs
-    if (blockIdx.x == 0 && i < a.world) st_release_sys(a.flags_of[i] + a.rank, epoch);
+    const long long lbase = a.recv_off + (long long)(epoch & 1u) * DP_MAX_WORLD * a.slot_floats;
+    const float* mine = a.sym[a.rank];
     if (i < a.world) {
-      const unsigned int* f = a.flags_of[a.rank] + i;
+      const unsigned int* f = reinterpret_cast<const unsigned int*>(mine + a.flagsb_off) +
+                              (long long)i * a.n_blocks + blockIdx.x;     // source rank i, this block
       const long long t0 = clock64();
       while ((int)(ld_acquire_sys(f) - epoch) < 0) {       // epochs only grow; signed difference tolerates wrap
         if (clock64() - t0 > a.timeout_cycles) {
@@ -200,11 +238,12 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
       }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(RED_IDX));
+    tstamp(3);
     g = 0.f;
     if (s_ok && idx < P.P) {
 #pragma unroll
-      for (int r = 0; r < DP_MAX_WORLD; ++r)
-        if (r < a.world) g += a.sym[r][soff + idx];           // fixed order: replicas stay bit-identical
+      for (int r = 0; r < DP_MAX_WORLD; ++r)                   // fixed order: replicas stay bit-identical
+        if (r < a.world) g += __ldcg(mine + lbase + (long long)r * a.slot_floats + idx);
       grad[idx] = g;
     }
     const float sq = warp_sum(g * g);
@@ -217,10 +256,12 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
       if (blockIdx.x == 0) {
         const int lo = (P.P + 3) & ~3;
         float l = 0.f;
-        for (int r = 0; r < a.world; ++r) l += a.sym[r][soff + lo];
+        for (int r = 0; r < a.world; ++r) l += __ldcg(mine + lbase + (long long)r * a.slot_floats + lo);
         loss[0] = s_ok ? l : __int_as_float(0x7fc00000);
       }
+      tstamp(4);
       grid_barrier(grid_bar, false);
+      tstamp(5);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(RED_IDX));
   }
@@ -260,6 +301,7 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
   }
   // every block read step[0] before the barrier
   if (blockIdx.x == 0 && i == 0) step[0] = t + 1;
+  tstamp(6);
 }
 
 }  // namespace mafb
