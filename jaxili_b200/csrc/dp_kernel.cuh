@@ -169,7 +169,7 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
   float g = 0.f;
   if (p == 0) {
     if (idx < P.P) {
-      g = ((red[0][i] + red[1][i]) + (red[2][i] + red[3][i]));
+      g = red_parts_sum(red, i);
       g = mk ? g : 0.f;
       if (DP) {
 #pragma unroll

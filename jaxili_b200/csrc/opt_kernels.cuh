@@ -18,8 +18,14 @@ struct OptArgs {
   int kind;
 };
 
-constexpr int RED_IDX = 256;    // parameters per reduction block
-constexpr int RED_PARTS = 4;    // threads cooperating on one parameter
+constexpr int RED_IDX = 128;    // parameters per reduction block (181 blocks for the narrow configs: every SM busy)
+constexpr int RED_PARTS = 8;    // threads cooperating on one parameter
+
+// fixed-order pairwise sum of the RED_PARTS partial sums of parameter i
+__device__ __forceinline__ float red_parts_sum(const float (&red)[RED_PARTS][RED_IDX], int i) {
+  static_assert(RED_PARTS == 8, "pairwise tree below is written for 8 parts");
+  return ((red[0][i] + red[1][i]) + (red[2][i] + red[3][i])) + ((red[4][i] + red[5][i]) + (red[6][i] + red[7][i]));
+}
 
 // flat index -> (layer, linear, k, n); returns true for a bias entry
 __device__ __forceinline__ bool decode_param(const Plan& P, int idx, int& layer, int& li, int& k, int& n) {
@@ -92,7 +98,7 @@ reduce_kernel(const float* __restrict__ partial, int G, int P, const unsigned ch
   if (p == 0) {
     float tot = 0.f;
     if (idx < P) {
-      tot = ((red[0][i] + red[1][i]) + (red[2][i] + red[3][i]));
+      tot = red_parts_sum(red, i);
       tot = mask[idx] ? tot : 0.f;
       grad[idx] = tot;
     }
