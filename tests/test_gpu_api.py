@@ -248,6 +248,9 @@ def test_npe_end_to_end(tmp_path):
     assert metrics["val/loss"] < float(-fresh.mean()) - 0.5
     lp = posterior.unnormalized_log_prob(s[:100])
     assert lp.shape == (100,)
+    # chunked delivery to pinned host memory == the one-shot draw, value for value
+    host = posterior.sample_to_host(5000, key=1, chunk_rows=1536)
+    assert host.is_pinned() and torch.equal(host, s.cpu())
     with pytest.raises(ValueError):
         posterior.unnormalized_log_prob(s[:100], x=x[:7])
 
