@@ -267,6 +267,7 @@ class TrainerModule:
         self._bufs = {}
         self._buf_events = {}
         self._pipeline = None
+        self._pipelines = {}
 
     # ------------------------------------------------------------------ setup
     def init_logger(self, logger_params: Optional[Dict] = None):
@@ -560,9 +561,13 @@ class TrainerModule:
 
     def host_pipeline(self, rows):
         """The (cached) ``HostBatchPipeline`` for batches of ``rows`` rows and the current optimiser state."""
-        p = self._pipeline
-        if p is None or p.rows != rows or p.t.state is not self.state or p.flat is not self.state.params.flat:
-            p = self._pipeline = HostBatchPipeline(self, rows)
+        cache = self._pipelines
+        p = cache.get(rows)
+        if p is None or p.t.state is not self.state or p.flat is not self.state.params.flat:
+            if p is None and len(cache) >= 4:        # a loader has at most a full and a ragged batch size
+                cache.clear()
+            p = cache[rows] = HostBatchPipeline(self, rows)
+        self._pipeline = p
         return p
 
     def _train_epoch_streamed(self, train_loader, num_train_steps, start_time):

@@ -201,6 +201,14 @@ def test_streamed_epoch_equals_plain_steps(tmp_path):
             assert abs(o[0] - outs[0][0]) < 1e-5 and abs(o[1] - outs[0][1]) < 1e-5
             assert torch.equal(o[2], outs[0][2])
         assert outs[0][1] < outs[0][0]             # it trains
+    # a ragged last batch (drop_last=False loaders) gets its own pipeline; both stay cached
+    ragged = np_loader + [[theta[:100], x[:100]]]
+    a, b = mk(loss_nll_npe, False), mk(loss_nll_npe, True)
+    ma, mb = a.train_epoch(ragged), b.train_epoch(ragged)
+    mb2, ma2 = b.train_epoch(ragged), a.train_epoch(ragged)
+    assert sorted(b._pipelines) == [100, 256]
+    assert abs(ma["train/loss"] - mb["train/loss"]) < 1e-5 and abs(ma2["train/loss"] - mb2["train/loss"]) < 1e-5
+    assert torch.equal(a.state.params.flat, b.state.params.flat)
 
 
 def test_npe_end_to_end(tmp_path):
