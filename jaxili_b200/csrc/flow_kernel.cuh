@@ -194,9 +194,9 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
   //      (no log-det accumulation, no hand-off of v to the next layer).
   auto layer_forward = [&](int k, const float* wf, float* slot, bool replay) {
     const float* in = sm + P.o_xin + k * P.xin_stride;
-#pragma unroll
-    for (int i = 0; i < (NLIN > 0 ? NLIN : MAFB_MAX_LIN); ++i) {
-      if (NLIN == 0 && i >= n_lin) break;
+    constexpr int kUnrollLin = NLIN > 0 ? NLIN : 1;     // NLIN == 0: rolled loop over the linears
+#pragma unroll kUnrollLin
+    for (int i = 0; i < (NLIN > 0 ? NLIN : n_lin); ++i) {
       const LinDesc& ln = P.lin[i];
       const float* W = wf + ln.w_off;
       const float* bias = wf + ln.b_off;
@@ -380,10 +380,10 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
           stamp(5);
         }
 
-#pragma unroll
-        for (int ii = 0; ii < (NLIN > 0 ? NLIN : MAFB_MAX_LIN); ++ii) {
+        constexpr int kUnrollLinB = NLIN > 0 ? NLIN : 1;
+#pragma unroll kUnrollLinB
+        for (int ii = 0; ii < (NLIN > 0 ? NLIN : n_lin); ++ii) {
           const int i = n_lin - 1 - ii;
-          if (NLIN == 0 && i < 0) break;
           const LinDesc& ln = P.lin[i];
           const float* G = (i == n_lin - 1) ? obuf : sm + P.o_g[i & 1];
           const float* Ain = (i == 0) ? xin : slot + P.h_off[i];

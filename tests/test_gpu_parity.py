@@ -291,3 +291,29 @@ def test_train_step_equals_loss_grad_plus_clip_adam(name, B, kind):
     for i in range(1, 5):
         assert torch.equal(a[i], b[i]), i
     assert b[0][-1] < b[0][0]
+
+
+@pytest.mark.parametrize("cfg,B,act", [
+    (dict(n_in=4, n_cond=3, n_layers=3, layers=[24]), 333, "relu"),             # one hidden layer: 2 masked linears
+    (dict(n_in=6, n_cond=2, n_layers=2, layers=[40, 24, 16]), 129, "tanh"),     # three hidden layers: 4 masked linears
+    (dict(n_in=5, n_cond=0, n_layers=3, layers=[32, 32, 32, 32]), 64, "silu"),  # unconditional, 5 masked linears
+])
+def test_other_depths_use_the_rolled_kernel(cfg, B, act):
+    """`layers` of any length >= 1: the kernel is specialised for 3 masked linears per MADE and runs a
+    rolled loop over the linears otherwise; forward, gradients and the conditioner gradient against the oracle."""
+    spec, flat, std, x, y = make_case(cfg, B, seed=31, activation=act)
+    eng = _engine(spec, std)
+    yt = _t(y) if cfg["n_cond"] else None
+    lp = eng.log_prob(_t(flat), _t(x), yt)
+    ref = onp.nde_log_prob(spec, flat.astype(np.float64), std, x.astype(np.float64), y.astype(np.float64))
+    assert rel_err(lp.cpu().numpy(), ref) < TOL
+    loss, grad = torch.zeros(1, device="cuda:0"), torch.zeros(spec.n_params, device="cuda:0")
+    eng.loss_grad(_t(flat), _t(x), yt, loss, grad)
+    l_ref, g_ref = onp.nll_loss_and_grad(spec, flat.astype(np.float64), std, x.astype(np.float64), y.astype(np.float64))
+    assert rel_err(loss.item(), l_ref) < TOL and grad_err(grad.cpu().numpy(), g_ref) < (1e-3 if act == "relu" else TOL)
+    # forward then inverse returns the input; the log-determinants cancel (jaxili/tests/test_nn.py:35-41)
+    u, ld = eng.forward(_t(flat), _t(x), yt)
+    back, ld_inv = eng.inverse(_t(flat), u, yt)
+    scale = np.abs(x).max()
+    assert np.max(np.abs(back.cpu().numpy() - x)) < 2e-5 * max(1.0, scale) * 10
+    assert torch.allclose(ld, -ld_inv, atol=1e-4)
