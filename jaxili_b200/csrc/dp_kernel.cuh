@@ -34,8 +34,7 @@ struct DpArgs {
   long long timeout_cycles;
   long long* trace;                       // debug (nullable): %globaltimer stamps of block 0 in step_tail_kernel
   // push protocol of step_tail_kernel<true>: every rank owns a receive area [2 parities][DP_MAX_WORLD sources]
-  // [slot_floats] at float offset recv_off of its symmetric buffer and per-(source, block) epoch flags at
-  // float offset flagsb_off ([DP_MAX_WORLD][n_blocks] u32)
+  // [slot_floats] of 64-bit words {value, epoch} at float offset recv_off of its symmetric buffer
   long long recv_off, flagsb_off;
   int n_blocks;
 };
@@ -44,6 +43,18 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+// 64-bit {value, epoch} words: a naturally aligned 64-bit store is single-copy atomic, so a reader that sees the
+// expected epoch in the upper half has the value in the lower half -- no fence, no separate flag (the idea of
+// NCCL's LL protocol), one NVLink one-way latency instead of store + fence + flag round trips
+__device__ __forceinline__ void st_ll(unsigned long long* p, float v, unsigned int epoch) {
+  const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_ll(const unsigned long long* p) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
 }
 __device__ __forceinline__ void st_relaxed_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -149,7 +160,8 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
   // DP: the locally reduced gradient is PUSHED into every rank's receive area of the coming epoch
   // (= count + 1; parity alternates): remote stores are fire-and-forget, the later sum reads local memory only
   const unsigned int epoch = (unsigned int)t + 1u;
-  const long long roff = DP ? a.recv_off + ((long long)(epoch & 1u) * DP_MAX_WORLD + a.rank) * a.slot_floats : 0;
+  // index (in 64-bit words) of this rank's lane in a receive area of the epoch's parity
+  const long long roff = DP ? ((long long)(epoch & 1u) * DP_MAX_WORLD + a.rank) * a.slot_floats : 0;
   float s = 0.f;
   if (idx < P.P) {
     const float* src = partial + idx;
@@ -174,7 +186,8 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
       if (DP) {
 #pragma unroll
         for (int r = 0; r < DP_MAX_WORLD; ++r)
-          if (r < a.world) const_cast<float*>(a.sym[r])[roff + idx] = g;
+          if (r < a.world)
+            st_ll(reinterpret_cast<unsigned long long*>(const_cast<float*>(a.sym[r]) + a.recv_off) + roff + idx, g, epoch);
       } else {
         grad[idx] = g;
       }
@@ -200,7 +213,9 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
       float l = 0.f;
       for (int w = 0; w < RED_IDX / 32; ++w) l += lsum[w];
       if (DP) {
-        for (int r = 0; r < a.world; ++r) const_cast<float*>(a.sym[r])[roff + ((P.P + 3) & ~3)] = l;
+        for (int r = 0; r < a.world; ++r)
+          st_ll(reinterpret_cast<unsigned long long*>(const_cast<float*>(a.sym[r]) + a.recv_off) + roff + ((P.P + 3) & ~3),
+                l, epoch);
       } else {
         loss[0] = l;
       }
@@ -209,43 +224,38 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
     tstamp(1);
     if (!DP) grid_barrier(grid_bar, false);
   }
-  if (DP && threadIdx.x < a.world) {
-    // this block's 256 entries are on their way to every rank: ONE system-scope fence for the warp (cumulative
-    // over the block's stores, which the __syncthreads above ordered before these lanes), then lane r raises
-    // the block's epoch flag on rank r with a relaxed store -- a release store per flag would repeat the fence
-    // and serialise one NVLink round trip per peer.  No grid barrier: block b only needs the peers' block b.
-    __threadfence_system();
-    st_relaxed_sys(reinterpret_cast<unsigned int*>(const_cast<float*>(a.sym[threadIdx.x]) + a.flagsb_off) +
-                       (long long)a.rank * a.n_blocks + blockIdx.x,
-                   epoch);
-  }
   tstamp(2);
   __syncthreads();
   if (p != 0) return;
   if (DP) {
-    const long long lbase = a.recv_off + (long long)(epoch & 1u) * DP_MAX_WORLD * a.slot_floats;
-    const float* mine = a.sym[a.rank];
-    if (i < a.world) {
-      const unsigned int* f = reinterpret_cast<const unsigned int*>(mine + a.flagsb_off) +
-                              (long long)i * a.n_blocks + blockIdx.x;     // source rank i, this block
-      const long long t0 = clock64();
-      while ((int)(ld_acquire_sys(f) - epoch) < 0) {       // epochs only grow; signed difference tolerates wrap
+    // every value arrives together with its epoch: spin on the 64-bit word itself (local memory)
+    const unsigned long long* mine =
+        reinterpret_cast<const unsigned long long*>(a.sym[a.rank] + a.recv_off) +
+        (long long)(epoch & 1u) * DP_MAX_WORLD * a.slot_floats;
+    const long long t0 = clock64();
+    auto take = [&](long long word) -> float {
+      unsigned long long w = ld_ll(mine + word);
+      while ((unsigned int)(w >> 32) != epoch) {
         if (clock64() - t0 > a.timeout_cycles) {
           s_ok = 0;
           *a.error = 1u;
           break;
         }
+        w = ld_ll(mine + word);
       }
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(RED_IDX));
+      return __uint_as_float((unsigned int)w);
+    };
     tstamp(3);
     g = 0.f;
-    if (s_ok && idx < P.P) {
+    if (idx < P.P) {
 #pragma unroll
       for (int r = 0; r < DP_MAX_WORLD; ++r)                   // fixed order: replicas stay bit-identical
-        if (r < a.world) g += __ldcg(mine + lbase + (long long)r * a.slot_floats + idx);
+        if (r < a.world) g += take((long long)r * a.slot_floats + idx);
       grad[idx] = g;
     }
+    float l_tot = 0.f;
+    if (blockIdx.x == 0 && i == 0)
+      for (int r = 0; r < a.world; ++r) l_tot += take((long long)r * a.slot_floats + ((P.P + 3) & ~3));
     const float sq = warp_sum(g * g);
     if ((i & 31) == 0) wsum[i >> 5] = sq;
     asm volatile("bar.sync 1, %0;" ::"n"(RED_IDX));
@@ -253,12 +263,7 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
       float tt = 0.f;
       for (int w = 0; w < RED_IDX / 32; ++w) tt += wsum[w];
       normpart[blockIdx.x] = tt;
-      if (blockIdx.x == 0) {
-        const int lo = (P.P + 3) & ~3;
-        float l = 0.f;
-        for (int r = 0; r < a.world; ++r) l += __ldcg(mine + lbase + (long long)r * a.slot_floats + lo);
-        loss[0] = s_ok ? l : __int_as_float(0x7fc00000);
-      }
+      if (blockIdx.x == 0) loss[0] = s_ok ? l_tot : __int_as_float(0x7fc00000);
       tstamp(4);
       grid_barrier(grid_bar, false);
       tstamp(5);

@@ -321,10 +321,10 @@ bool make_sample_plan(const MafDesc& d, const int* dims, SamplePlan& S) {
 }  // namespace
 
 static size_t dp_slot_floats(const Plan& P) { return (size_t)((P.P + 3) & ~3) + 4; }
-// symmetric buffer (floats): [2][sf] own slots (pull protocol) | [8] flags | [2][8][sf] receive area (push
-// protocol of step_tail_kernel) | [8][n_blocks] per-(source, block) flags
+// symmetric buffer (floats): [2][sf] own slots (pull protocol) | [8] flags | [2][8][sf] 64-bit {value, epoch}
+// words = receive area of the push protocol of step_tail_kernel | [8][n_blocks] spare flags
 static size_t dp_recv_off(const Plan& P) { return 2 * dp_slot_floats(P) + 8; }
-static size_t dp_flagsb_off(const Plan& P) { return dp_recv_off(P) + 2 * DP_MAX_WORLD * dp_slot_floats(P); }
+static size_t dp_flagsb_off(const Plan& P) { return dp_recv_off(P) + 2 * (2 * DP_MAX_WORLD * dp_slot_floats(P)); }   // 64-bit words
 static size_t dp_total_floats(const Plan& P, int n_blocks) { return dp_flagsb_off(P) + (size_t)DP_MAX_WORLD * n_blocks; }
 
 template <bool BWD>
@@ -963,7 +963,9 @@ int mafb200_dp_reset(mafb200_handle h) {
   CU(cudaSetDevice(h->device));
   CU(cudaDeviceSynchronize());
   CU(cudaMemset(h->dp_flags, 0, DP_MAX_WORLD * sizeof(unsigned int)));
-  CU(cudaMemset(h->dp_sym + dp_flagsb_off(h->plan), 0, (size_t)DP_MAX_WORLD * h->n_norm * sizeof(unsigned int)));
+  // receive area too: a rewound step counter must never match the epoch of a value left by an earlier run
+  CU(cudaMemset(h->dp_sym + dp_recv_off(h->plan), 0,
+                (dp_total_floats(h->plan, h->n_norm) - dp_recv_off(h->plan)) * sizeof(float)));
   CU(cudaMemset(h->dp_error, 0, 4));
   CU(cudaDeviceSynchronize());
   return 0;

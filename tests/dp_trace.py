@@ -24,11 +24,26 @@ eng = tr.model.engine()
 dev = torch.device("cuda", local)
 td, xd = torch.tensor(theta, device=dev), torch.tensor(x, device=dev)
 trace = torch.zeros(1001, dtype=torch.int64, device=dev)
+eng.lib.mafb200_debug_trace(eng._h, C.c_void_p(trace.data_ptr()))     # before capture: the graph bakes the pointer
 step = tr.make_graph_step(td, xd, B)
 for _ in range(20):
     step()
 torch.cuda.synchronize(); dist.barrier()
-eng.lib.mafb200_debug_trace(eng._h, C.c_void_p(trace.data_ptr()))
+# steady-state graph replay: the stamps of the last step survive; sample a few by syncing every 50 steps
+g_rows = []
+for rep in range(6):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    t = trace[900:907].cpu().numpy()
+    g_rows.append([e0.elapsed_time(e1) * 1e3 / 50] + [(t[k] - t[0]) / 1e3 for k in range(1, 7)])
+if rank == 0:
+    print("GRAPH mode: step_us | stage1 done, flags raised, peers seen, summed, barrier B, end")
+    for r in g_rows:
+        print("G " + " ".join(f"{v:8.2f}" for v in r))
+dist.barrier()
 # the graph baked a null trace pointer: run eager steps for the stamps
 st = tr.state
 flat = st.params.flat
