@@ -1,4 +1,5 @@
-// dp_kernel.cuh -- one-shot all-reduce of the flat gradient over NVLink peer memory, fused with the
+// dp_kernel.cuh -- one-shot all-reduce of the flat gradient over NVLink peer memory (pull kernel below, and the
+// push exchange inside step_tail_kernel<DP> further down), fused with the
 // squared-norm partials the clip needs.
 //
 // Data-parallel training exchanges P floats (+ the loss) per step: 92 KB for the narrow configs.  At
