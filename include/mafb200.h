@@ -75,7 +75,8 @@ enum {
      skip the norm launch. */
   MAFB200_NORM_CURRENT = 2,
   /* loss_grad: write the reduced gradient and loss into this rank's symmetric (peer-mapped) slot
-     instead of out_grad / out_loss; mafb200_dp_allreduce then sums the ranks' slots. */
+     instead of out_grad / out_loss; mafb200_dp_allreduce then sums the ranks' slots.
+     train_step / pipeline_create: data-parallel step, the exchange runs inside the tail kernel. */
   MAFB200_DP_SLOT = 4
 };
 
@@ -157,10 +158,14 @@ int mafb200_flow_elapsed(mafb200_handle h, double* total_ms, int64_t* launches);
    exchanges handles (e.g. torch.distributed.all_gather) and passes all of them, rank-major, to
    dp_connect; dp_bind_step names the device step counter (the exchange epoch and the slot parity are
    derived from it on the device, so the whole step is CUDA-graph capturable).
-   Per step: loss_grad(..., MAFB200_DP_SLOT) -> dp_allreduce -> clip_adam(..., MAFB200_NORM_CURRENT).
-   dp_allreduce is a one-shot all-reduce (every rank reads every peer's slot) in a fixed rank order, so
-   replicas stay bit-identical; it replaces ncclAllReduce for this latency-bound message.  Every rank
-   must call it the same number of times.  dp_error reports a peer time-out (synchronises). */
+   Per step, either  train_step(..., MAFB200_DP_SLOT)  -- two launches; the tail kernel pushes every reduced
+   gradient entry to all peers as a 64-bit {value, epoch} word and sums the world's words locally --
+   or the three-call form  loss_grad(..., MAFB200_DP_SLOT) -> dp_allreduce -> clip_adam(..., MAFB200_NORM_CURRENT),
+   where dp_allreduce is a one-shot pull all-reduce (every rank reads every peer's slot).  Both sum in a
+   fixed rank order, so replicas stay bit-identical, and replace ncclAllReduce for this latency-bound
+   message.  Every rank must make the same calls the same number of times.  dp_reset (between host
+   barriers) forgets all epochs: required whenever the step counter is replaced or rewound.  dp_error
+   reports a peer time-out (synchronises). */
 int mafb200_dp_init(mafb200_handle h, int32_t rank, int32_t world, void* ipc_handle_out);
 int mafb200_dp_connect(mafb200_handle h, const void* all_handles);
 int mafb200_dp_bind_step(mafb200_handle h, const int32_t* step);   /* device optax count = exchange epoch - 1 */

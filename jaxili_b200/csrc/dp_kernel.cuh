@@ -36,8 +36,7 @@ struct DpArgs {
   long long* trace;                       // debug (nullable): %globaltimer stamps of block 0 in step_tail_kernel
   // push protocol of step_tail_kernel<true>: every rank owns a receive area [2 parities][DP_MAX_WORLD sources]
   // [slot_floats] of 64-bit words {value, epoch} at float offset recv_off of its symmetric buffer
-  long long recv_off, flagsb_off;
-  int n_blocks;
+  long long recv_off;
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
@@ -56,9 +55,6 @@ __device__ __forceinline__ unsigned long long ld_ll(const unsigned long long* p)
   unsigned long long w;
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
   return w;
-}
-__device__ __forceinline__ void st_relaxed_sys(unsigned int* p, unsigned int v) {
-  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

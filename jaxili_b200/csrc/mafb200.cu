@@ -322,10 +322,9 @@ bool make_sample_plan(const MafDesc& d, const int* dims, SamplePlan& S) {
 
 static size_t dp_slot_floats(const Plan& P) { return (size_t)((P.P + 3) & ~3) + 4; }
 // symmetric buffer (floats): [2][sf] own slots (pull protocol) | [8] flags | [2][8][sf] 64-bit {value, epoch}
-// words = receive area of the push protocol of step_tail_kernel | [8][n_blocks] spare flags
+// words = receive area of the push protocol of step_tail_kernel
 static size_t dp_recv_off(const Plan& P) { return 2 * dp_slot_floats(P) + 8; }
-static size_t dp_flagsb_off(const Plan& P) { return dp_recv_off(P) + 2 * (2 * DP_MAX_WORLD * dp_slot_floats(P)); }   // 64-bit words
-static size_t dp_total_floats(const Plan& P, int n_blocks) { return dp_flagsb_off(P) + (size_t)DP_MAX_WORLD * n_blocks; }
+static size_t dp_total_floats(const Plan& P) { return dp_recv_off(P) + 2 * (2 * DP_MAX_WORLD * dp_slot_floats(P)); }
 
 template <bool BWD>
 static void launch_flow(const Plan& P, const FlowArgs& A, int grid, cudaStream_t st) {
@@ -890,7 +889,7 @@ int mafb200_dp_init(mafb200_handle h, int32_t rank, int32_t world, void* ipc_han
   if (world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world) return fail("bad rank / world (max 8)");
   if (h->dp_sym) return fail("dp already initialised");
   CU(cudaSetDevice(h->device));
-  const size_t bytes = dp_total_floats(h->plan, h->n_norm) * 4;
+  const size_t bytes = dp_total_floats(h->plan) * 4;
   CU(cudaMalloc(&h->dp_sym, bytes));
   CU(cudaMemset(h->dp_sym, 0, bytes));
   CU(cudaMalloc(&h->dp_error, 4));
@@ -965,7 +964,7 @@ int mafb200_dp_reset(mafb200_handle h) {
   CU(cudaMemset(h->dp_flags, 0, DP_MAX_WORLD * sizeof(unsigned int)));
   // receive area too: a rewound step counter must never match the epoch of a value left by an earlier run
   CU(cudaMemset(h->dp_sym + dp_recv_off(h->plan), 0,
-                (dp_total_floats(h->plan, h->n_norm) - dp_recv_off(h->plan)) * sizeof(float)));
+                (dp_total_floats(h->plan) - dp_recv_off(h->plan)) * sizeof(float)));
   CU(cudaMemset(h->dp_error, 0, 4));
   CU(cudaDeviceSynchronize());
   return 0;
@@ -1339,8 +1338,6 @@ int mafb200_train_step(mafb200_handle h, float* params, const float* x, const fl
     a.error = h->dp_error;
     a.timeout_cycles = 4000000000LL;
     a.recv_off = (long long)dp_recv_off(Pk);
-    a.flagsb_off = (long long)dp_flagsb_off(Pk);
-    a.n_blocks = h->n_norm;
   }
   a.trace = h->trace ? h->trace + 900 : nullptr;
   void* args[] = {&Pk, &O, &partial, &grid, &mask, &out_grad, &ploss, &out_loss, &normpart, &params,
