@@ -131,7 +131,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, bool syste
 }
 
 template <bool DP>
-__global__ void __launch_bounds__(RED_IDX * RED_PARTS)
+__global__ void __launch_bounds__(RED_IDX * RED_PARTS, 2)   // two blocks per SM: all ceil(P/128) blocks co-resident
 step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs O, const float* __restrict__ partial,
                  int G, const unsigned char* __restrict__ mask, float* __restrict__ grad,
                  const float* __restrict__ partial_loss, float* __restrict__ loss, float* __restrict__ normpart,
