@@ -307,3 +307,28 @@ def test_mcmc_host_pieces():
     assert post.log_prior(t).shape == (2,)
     with pytest.raises(ValueError):
         post.sample(10)
+
+
+def test_utils_like_reference():
+    """jaxili/tests/test_utils.py:6-49 against the shims (the realnvp / mdn hyper-parameter checks belong to
+    density estimators outside this path)."""
+    from jaxili_b200 import nn
+    from jaxili_b200.utils import check_density_estimator, check_hparams_maf, validate_theta_x
+    check_density_estimator("maf")
+    check_density_estimator("mdn")
+    check_density_estimator("realnvp")
+    with pytest.raises(ValueError):
+        check_density_estimator("blablabla")
+    rng = np.random.default_rng(0)
+    theta = rng.standard_normal((100, 2)).astype(np.float32)
+    x = rng.standard_normal((100, 2)).astype(np.float32)
+    validate_theta_x(torch.from_numpy(theta), torch.from_numpy(x))
+    _, _, batch_size = validate_theta_x(theta, x)
+    assert batch_size == 100
+    with pytest.raises(AssertionError):
+        validate_theta_x(theta, x[1:])
+    check_hparams_maf({"n_layers": 5, "layers": [50, 50, 50], "activation": nn.relu, "use_reverse": True})
+    with pytest.raises(AssertionError):
+        check_hparams_maf({})
+    with pytest.raises(AssertionError):
+        check_hparams_maf({"n_layers": 5.0, "layers": [50], "activation": nn.relu, "use_reverse": True})
