@@ -114,6 +114,7 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
   stamp(0);
 
   const bool recompute = BWD && !P.stash_all;
+  const bool two_wbuf = P.n_wbuf == 2;
   const int per_tile = BWD ? 2 * L : L;
   const int total_req = my_n * per_tile;
 
@@ -128,7 +129,7 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
     if (part == 0) bytes = P.fwd_floats * 4u;
     else if (recompute) bytes = P.img_floats * 4u;
     else { src += P.fwd_floats; bytes = P.bwd_floats * 4u; }
-    const int buf = s % P.n_wbuf;
+    const int buf = two_wbuf ? (s & 1) : 0;
     mbar_expect_tx(&wbar[buf], bytes);
     bulk_g2s(sm + P.o_wbuf + buf * P.wbuf_stride, src, bytes, &wbar[buf]);
   };
@@ -136,12 +137,12 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
   // every thread: make request s resident, prefetch s+1; returns the buffer.  The buffer being
   // refilled was last read before the __syncthreads that precedes this call.
   auto w_acquire = [&](int s) -> const float* {
-    const int buf = s % P.n_wbuf;
+    const int buf = two_wbuf ? (s & 1) : 0;       // n_wbuf is 1 or 2: no integer division on this path
     if (issuer) {
       if (P.n_wbuf == 1) w_issue(s);
       else if (s + 1 < total_req) w_issue(s + 1);
     }
-    mbar_wait(&wbar[buf], (uint32_t)((s / P.n_wbuf) & 1));
+    mbar_wait(&wbar[buf], (uint32_t)(two_wbuf ? (s >> 1) & 1 : s & 1));
     return sm + P.o_wbuf + buf * P.wbuf_stride;
   };
 

@@ -24,7 +24,7 @@ else: eng.log_prob(p, xt, yt, packed_current=True)
 torch.cuda.synchronize()
 tr = trace.cpu().numpy(); n = int(tr[1000])
 ids = tr[0:2*n:2]; clk = tr[1:2*n:2]
-names = {40:"  X start",41:"  X done",42:"  B start",43:"  B done",30:" mm start",31:" mm done",32:" scatter done",33:" epilogue done",0:"start",1:"stage ready",2:"transpose done",3:"W fwd acquired",4:"W bwd acquired",5:"bwd elementwise",6:"finalize",19:"fwd affine",99:"end"}
+names = {50:"   acq: before wait",51:"   acq: after wait",40:"  X start",41:"  X done",42:"  B start",43:"  B done",30:" mm start",31:" mm done",32:" scatter done",33:" epilogue done",0:"start",1:"stage ready",2:"transpose done",3:"W fwd acquired",4:"W bwd acquired",5:"bwd elementwise",6:"finalize",19:"fwd affine",99:"end"}
 prev = clk[0]
 for i in range(n):
     nm = names.get(int(ids[i]), ("fwd lin %d" % (ids[i]-10)) if 10 <= ids[i] < 19 else ("bwd lin %d" % (ids[i]-20)))
