@@ -316,24 +316,55 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
     }
 
     // ---- log-probability per row (jaxili/model.py:919-921 + 1094-1098); seed of the reverse pass
-    for (int r = tid; r < ((Rt + 31) & ~31); r += NT) {   // whole warps: lane = row
-      float acc = 0.f, ldsum = 0.f;
-      if (r < Rt)
+    if (BWD) {
+      // all warps: RPW rows per warp, LPR lanes per row striding the features; the row sums go through an xor
+      // shuffle tree (fixed order).  With every layer's (s, v) stashed the last layer's elementwise reverse step
+      // (gradient w.r.t. mu | logp and the direct path) is done right here, saving a phase.
+      constexpr int RPW = 32 / NW, LPR = 32 / RPW;        // 512 threads: 2 x 16, 256 threads: 4 x 8
+      const int r = warp * RPW + lane / LPR;
+      const int f0 = lane % LPR;
+      const bool rok = r < Rt, vok = r < valid;
+      const bool fuse_fin = P.stash_all != 0;
+      const float* pslot = sm + P.o_slot + (P.stash_all ? L - 1 : 0) * P.slot_stride;
+      float* gx_l = gx + ((L - 1) & 1) * P.DP * RP;
+      float acc = 0.f;
+      if (rok)
+        for (int j = f0; j < D; j += LPR) {
+          const float u = gu[j * RP + r];
+          const float l = ld[j * RP + r];
+          acc += l - 0.5f * u * u;
+          const float gv = vok ? u * A.inv_b : 0.f;
+          gu[j * RP + r] = gv;
+          if (fuse_fin) {
+            const int jm = P.reverse ? D - 1 - j : j;      // output j of the flow is MADE feature jm of the last layer
+            const float s = pslot[P.s_off + jm * RP + r], v = pslot[P.v_off + jm * RP + r];
+            obuf[jm * RP + r] = vok ? -gv * s : 0.f;
+            obuf[(D + jm) * RP + r] = vok ? 0.5f * gv * v - 0.5f * A.inv_b : 0.f;
+            gx_l[jm * RP + r] = vok ? gv * s : 0.f;
+          }
+        }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const float lp = acc - (float)D * kHalfLog2Pi + A.logdet_const;
+      const bool lead = f0 == 0 && vok;
+      if (lead && A.out_logp) A.out_logp[row0 + r] = lp;
+      const float contrib = warp_sum(lead ? -lp * A.inv_b : 0.f);
+      if (lane == 0) sm[P.o_red + warp] = contrib;
+    }
+    if (!BWD) {
+      for (int r = tid; r < Rt; r += NT) {   // forward only: lane = row
+        float acc = 0.f, ldsum = 0.f;
         for (int j = 0; j < D; ++j) {
           const float u = gu[j * RP + r];
           const float l = ld[j * RP + r];
           ldsum += l;
           acc += l - 0.5f * u * u;
-          if (BWD) gu[j * RP + r] = r < valid ? u * A.inv_b : 0.f;
         }
-      const float lp = acc - (float)D * kHalfLog2Pi + A.logdet_const;
-      if (BWD) {
-        const float contrib = warp_sum(r < valid ? -lp * A.inv_b : 0.f);
-        if (lane == 0) atomicAdd(loss_acc, contrib);
-        if (A.out_logp && r < valid) A.out_logp[row0 + r] = lp;
-      } else if (r < valid) {
-        if (A.out_logp) A.out_logp[row0 + r] = lp;
-        if (A.out_logdet) A.out_logdet[row0 + r] = ldsum;
+        const float lp = acc - (float)D * kHalfLog2Pi + A.logdet_const;
+        if (r < valid) {
+          if (A.out_logp) A.out_logp[row0 + r] = lp;
+          if (A.out_logdet) A.out_logdet[row0 + r] = ldsum;
+        }
       }
     }
     if (!BWD && A.out_u) {   // u rows are contiguous in HBM: coalesced store
@@ -344,6 +375,11 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
       }
     }
     __syncthreads();
+    if (BWD && tid == 0) {      // per-warp loss contributions in warp order: reproducible
+      float t = 0.f;
+      for (int w = 0; w < NW; ++w) t += sm[P.o_red + w];
+      *loss_acc += t;
+    }
     stamp(6);
 
     if (BWD) {
@@ -359,11 +395,11 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
         const float* xin = sm + P.o_xin + k * P.xin_stride;
 
         // gradient w.r.t. the MADE outputs (mu | logp) and the direct path to x.  With every layer's (s, v)
-        // stashed this runs as its own phase for the last layer only: for the others it is fused into the
-        // epilogue of the following layer's input-gradient product (below).
+        // stashed this never runs as its own phase: the last layer's is part of the finalize step above, the
+        // others are fused into the epilogue of the following layer's input-gradient product (below).
         const bool fuse_ew = P.stash_all != 0;
         float* gx_k = gx + (k & 1) * P.DP * RP;
-        if (!fuse_ew || k == L - 1) {
+        if (!fuse_ew) {
           const float* sbuf = slot + P.s_off;
           const float* vbuf = slot + P.v_off;
           for (int r = lane; r < Rt; r += 32) {

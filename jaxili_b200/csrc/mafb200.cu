@@ -180,6 +180,8 @@ bool plan_layout(Plan& P, int R, bool stash_all, int n_wbuf, int limit) {
   o += P.DP * RP;
   P.o_cst = o;
   o += r4(2 * P.D + 2 * P.C);
+  P.o_red = o;
+  o += 32;
   P.o_gy = o;
   o += (r4(P.K0) - P.DP + 4) * RP;        // conditioner rows of the padded MADE input (dy mode)
   P.o_g[0] = o;

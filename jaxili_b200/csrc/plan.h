@@ -43,6 +43,7 @@ struct Plan {
   int o_obuf;                   // [round4(2D)][RP]: MADE output, then grad wrt it
   int o_gu, o_gx, o_ld;         // [DP][RP] each (o_gx: two of them, ping-pong by layer parity)
   int o_cst;                    // standardisation constants [2D + 2C]
+  int o_red;                    // [32] per-warp loss contributions of the finalize step
   int o_gy;                     // [round4(C)][RP]: gradient w.r.t. the standardised conditioner (dy mode)
   int o_g[2];                   // ping-pong [max HP][RP] hidden-gradient buffers
   int smem_bytes;
