@@ -72,11 +72,28 @@ def setup_peer_allreduce(engine, step):
         return False
     if os.environ.get("MAFB200_NO_PEER"):        # force the NCCL path (A/B measurements)
         return False
+    if getattr(engine, "_dp_failed", False):
+        return False
     if not getattr(engine, "_dp_ready", False):
-        handle = engine.dp_init(rank, world)
+        # mapping the peers' buffers needs CUDA IPC + peer access (NVLink / NVSwitch boxes); if any rank cannot
+        # map them, every rank falls back to the NCCL all-reduce together
+        ok = 1
+        try:
+            handle = engine.dp_init(rank, world)
+        except Exception:
+            handle, ok = b"\0" * 64, 0
         handles = [None] * world
         dist.all_gather_object(handles, handle)
-        engine.dp_connect(handles)
+        if ok:
+            try:
+                engine.dp_connect(handles)
+            except Exception:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=engine.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            engine._dp_failed = True
+            return False
         engine._dp_ready = True
         engine._dp_step = None
     if engine._dp_step is None or engine._dp_step.data_ptr() != step.data_ptr():
