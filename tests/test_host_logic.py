@@ -332,3 +332,54 @@ def test_utils_like_reference():
         check_hparams_maf({})
     with pytest.raises(AssertionError):
         check_hparams_maf({"n_layers": 5.0, "layers": [50], "activation": nn.relu, "use_reverse": True})
+
+
+_PEER_FALLBACK_WORKER = r"""
+import sys, os
+root, rank, world, port = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+sys.path.insert(0, root)
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=port, RANK=str(rank), WORLD_SIZE=str(world))
+import torch, torch.distributed as dist
+dist.init_process_group("gloo", rank=rank, world_size=world)
+from jaxili_b200 import parallel
+
+class StubEngine:
+    # stands in for MafEngine: rank 1 cannot map its peers (no NVLink / IPC)
+    n_params = 1000
+    device = torch.device("cpu")
+    def __init__(self): self.calls = []
+    def dp_init(self, r, w): self.calls.append("init"); return bytes(64)
+    def dp_connect(self, handles):
+        self.calls.append("connect")
+        if rank == 1: raise RuntimeError("cudaIpcOpenMemHandle: peer access unsupported")
+    def dp_reset(self): self.calls.append("reset")
+    def dp_bind_step(self, s): self.calls.append("bind")
+
+eng = StubEngine()
+step = torch.zeros(1, dtype=torch.int32)
+parallel.torch.cuda.synchronize = lambda *a, **k: None      # CPU stand-in
+first = parallel.setup_peer_allreduce(eng, step)
+second = parallel.setup_peer_allreduce(eng, step)          # remembered: no second attempt, no collective
+assert first is False and second is False, (first, second)
+assert eng.calls == ["init", "connect"], eng.calls
+assert "reset" not in eng.calls and "bind" not in eng.calls
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_peer_mapping_failure_falls_back_on_every_rank(tmp_path):
+    """If ANY rank cannot map the peers' buffers, ALL ranks must take the NCCL path together (a split decision
+    would deadlock the first collective)."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "peer_worker.py"
+    script.write_text(_PEER_FALLBACK_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(r), "2", str(port)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    for p in procs:
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out.decode()[-2000:]
