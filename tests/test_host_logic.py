@@ -383,3 +383,23 @@ def test_peer_mapping_failure_falls_back_on_every_rank(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out.decode()[-2000:]
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: the header must compile as C99 (no C++ types in the signatures) and a C
+    program must link against the library and call a non-compute entry."""
+    hdr = os.path.join(ROOT, "include", "mafb200.h")
+    r = subprocess.run(["gcc", "-x", "c", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", hdr],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "mafb200.h"\n'
+                   'int main(void) { MafDesc d; d.n_in = 0; printf("%d %d\\n", mafb200_version(), (int)sizeof(d));\n'
+                   '  return mafb200_last_error() == 0; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "jaxili_b200", "csrc")
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-lmafb200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split()[0].isdigit(), (r.returncode, r.stdout, r.stderr)
