@@ -189,8 +189,9 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU arm (oracle port)
-def cpu_train_throughput(name, cfg, batch, budget_s, threads):
-    """Train steps of the CPU restatement (oracle/maf_torch.py) on `threads` host threads."""
+def cpu_train_throughput(name, cfg, batch, budget_s, threads, steps=None, warmup=3):
+    """Train steps of the CPU restatement (oracle/maf_torch.py) on `threads` host threads: `warmup` untimed
+    steps, then `steps` timed ones (all that fit `budget_s` seconds if None or too many)."""
     import torch
     from oracle import maf_numpy as onp
     from oracle.maf_torch import TorchMaf, TorchTrainer
@@ -203,11 +204,11 @@ def cpu_train_throughput(name, cfg, batch, budget_s, threads):
     tr = TorchTrainer(TorchMaf(spec, std), flat, lr=5e-4, warmup=0.1, decay_steps=1e9)
     xs = [torch.tensor(dv[i * batch:(i + 1) * batch]) for i in range(4)]
     ys = [torch.tensor(cv[i * batch:(i + 1) * batch]) for i in range(4)]
-    for i in range(3):
+    for i in range(max(1, warmup)):
         tr.train_step(xs[i % 4], ys[i % 4])
     t0 = time.perf_counter()
     n = 0
-    while time.perf_counter() - t0 < budget_s:
+    while time.perf_counter() - t0 < budget_s and (steps is None or n < steps):
         tr.train_step(xs[n % 4], ys[n % 4])
         n += 1
     dt = time.perf_counter() - t0
@@ -251,15 +252,18 @@ def run_reference_arm(args, name, cfg, batch):
         metric, steps = "posterior samples/sec", len(vals)
         ms = rows / value * 1e3
     else:
-        # bounded: each step is one full batch; K steps capped so the arm ends within ~1 minute
+        # bounded: each step is one full batch; W warm-up steps, then K timed steps -- capped at the steps that
+        # fit 20 s of CPU work so that the arm ends within a minute whatever K is
         budget = 20.0
-        value, n, dt = cpu_train_throughput(name, cfg, batch, budget, threads)
-        sample = f"{n} train steps of batch {batch} in {dt:.1f} s"
+        warm = max(1, min(args.warmup, 20))
+        value, n, dt = cpu_train_throughput(name, cfg, batch, budget, threads, steps=args.steps, warmup=warm)
+        sample = f"{n} train steps of batch {batch} in {dt:.1f} s" + \
+                 (f" ({args.steps} requested, capped by the {budget:.0f} s budget)" if n < args.steps else "")
         metric, steps = "MAF train samples/sec (fwd+bwd+clip+Adam)", n
         ms = batch / value * 1e3
     line = {
         "impl": "reference", "metric": metric, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": steps, "warmup": (max(1, min(args.warmup, 20)) if name != "c4" else 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[name][2], "batch": batch},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
