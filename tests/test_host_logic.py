@@ -403,3 +403,30 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.split()[0].isdigit(), (r.returncode, r.stdout, r.stderr)
+
+
+def test_kernel_resource_budgets():
+    """Regression guard on the built cubin (cuobjdump, no GPU): the fused flow kernels keep their accumulators in
+    registers (one 512-thread CTA per SM: <= 128 registers, no local-memory stack) and the cooperative tail kernel
+    stays at 32 registers, which is what lets all ceil(P/128) blocks be co-resident two per SM."""
+    import shutil
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.isfile(tool):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([tool, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        line = line.strip()
+        if line.startswith("Function "):
+            name = line[len("Function "):].rstrip(":")
+        elif line.startswith("REG:") and name:
+            usage[name] = {k: int(v) for k, v in (f.split(":") for f in line.split() if f.split(":")[1].isdigit())}
+    flow512 = {n: u for n, u in usage.items() if "maf_flow_kernel" in n and "ELi512E" in n}
+    assert len(flow512) >= 8
+    for n, u in flow512.items():
+        assert u["REG"] <= 128 and u["STACK"] == 0, (n, u)
+    tails = {n: u for n, u in usage.items() if "step_tail_kernel" in n}
+    assert len(tails) == 2 and all(u["REG"] <= 32 for u in tails.values()), tails
+    samplers = {n: u for n, u in usage.items() if "maf_sample_kernel" in n}
+    assert samplers and all(u["STACK"] == 0 for u in samplers.values()), samplers
