@@ -430,3 +430,28 @@ def test_kernel_resource_budgets():
     assert len(tails) == 2 and all(u["REG"] <= 32 for u in tails.values()), tails
     samplers = {n: u for n, u in usage.items() if "maf_sample_kernel" in n}
     assert samplers and all(u["STACK"] == 0 for u in samplers.values()), samplers
+
+
+def test_sass_shows_blackwell_native_paths():
+    """SASS of the built library (cuobjdump, no GPU): the wide GEMM core is tcgen05 (UTCHMMA tiles fed by UTMALDG,
+    accumulators read back with LDTM), the fused flow kernel stages its operands with bulk copies (UBLKCP) behind
+    mbarriers (SYNCS) and runs packed FFMA2 in its micro-GEMMs; no legacy tensor-core path (HMMA) anywhere."""
+    import shutil
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.isfile(tool):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([tool, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    per_fn, name = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+            per_fn[name] = set()
+        elif name:
+            for m in ("UTCHMMA", "UTMALDG", "LDTM", "UBLKCP", "SYNCS", "FFMA2", "HMMA"):
+                if m in line and not (m == "HMMA" and "UTCHMMA" in line):
+                    per_fn[name].add(m)
+    tc = [s for n, s in per_fn.items() if "wide_tc_gemm_kernel" in n]
+    assert tc and all({"UTCHMMA", "UTMALDG", "LDTM"} <= s for s in tc)
+    flow = [s for n, s in per_fn.items() if "maf_flow_kernel" in n]
+    assert flow and all({"UBLKCP", "SYNCS", "FFMA2"} <= s for s in flow)
+    assert not any("HMMA" in s for s in per_fn.values())
