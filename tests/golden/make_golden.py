@@ -37,6 +37,10 @@ def main():
         loss, grad = onp.nll_loss_and_grad(spec, f64, std, x64, y64)
         u = np.random.default_rng(5).standard_normal((32, spec.n_in)).astype(np.float32)
         samples = onp.nde_sample_from_noise(spec, f64, std, u.astype(np.float64), y[0])
+        # per-row gradient of log_prob w.r.t. the RAW conditioning input (the NLE / HMC entry point): the reverse
+        # pass with 1/B := -1 differentiates sum_b log p_b; d/dy = (d/dy') / std
+        _, _, gy = onp.nll_loss_and_grad(spec, f64, std, x64, y64, inv_b=-1.0, want_dy=True)
+        dlogp_dy = gy / std.std.astype(np.float64)
         st = onp.AdamState(f64.size, np.float64)
         p1, lr0, gn = onp.clip_adam_step(f64, grad, st, 5e-4, 0.1, 1e6, clip=5.0)
         np.savez_compressed(
@@ -45,7 +49,7 @@ def main():
             activation=act, use_reverse=rev, seed=42, layer_seeds=np.array(spec.seeds),
             flat=flat, x=x, y=y, shift=std.shift, scale=std.scale, mean=std.mean, std=std.std,
             logp=logp, loss=loss, grad=grad.astype(np.float32), u=u, samples=samples,
-            params_after_adam=p1.astype(np.float32), lr0=lr0, gnorm=gn)
+            params_after_adam=p1.astype(np.float32), lr0=lr0, gnorm=gn, dlogp_dy=dlogp_dy)
         print(tag, "P =", spec.n_params, "loss =", float(loss))
 
 

@@ -160,3 +160,10 @@ def test_oracle_reproduces_golden(path):
     assert rel_err(s, z["samples"]) < 1e-12
     ts = TorchMaf(spec, std, torch.float64).sample_from_noise(f64, z["u"].astype(np.float64), z["y"][0])
     assert rel_err(ts, z["samples"]) < 1e-10
+    # gradient of log_prob w.r.t. the raw conditioning input: hand-written reverse pass == stored == torch autograd
+    _, _, gy = onp.nll_loss_and_grad(spec, f64, std, z["x"].astype(np.float64), z["y"].astype(np.float64),
+                                     inv_b=-1.0, want_dy=True)
+    assert np.max(np.abs(gy / z["std"].astype(np.float64) - z["dlogp_dy"])) < 1e-12 * max(1.0, np.abs(z["dlogp_dy"]).max())
+    yt = torch.tensor(z["y"].astype(np.float64), requires_grad=True)
+    TorchMaf(spec, std, torch.float64).log_prob(torch.tensor(f64), torch.tensor(z["x"].astype(np.float64)), yt).sum().backward()
+    assert np.max(np.abs(yt.grad.numpy() - z["dlogp_dy"])) < 1e-9 * max(1.0, np.abs(z["dlogp_dy"]).max())
