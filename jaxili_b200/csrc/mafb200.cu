@@ -322,6 +322,9 @@ bool make_sample_plan(const MafDesc& d, const int* dims, SamplePlan& S) {
 
 }  // namespace
 
+// ~20 s at 1.9 GHz: long enough for a rank that is busy on the host (checkpoint, validation) to arrive, short
+// enough that a dead peer ends in an error word + NaN loss instead of a hung GPU
+constexpr long long kDpTimeoutCycles = 40000000000LL;
 static size_t dp_slot_floats(const Plan& P) { return (size_t)((P.P + 3) & ~3) + 4; }
 // symmetric buffer (floats): [2][sf] own slots (pull protocol) | [8] flags | [2][8][sf] 64-bit {value, epoch}
 // words = receive area of the push protocol of step_tail_kernel
@@ -945,7 +948,7 @@ int mafb200_dp_allreduce(mafb200_handle h, float* grad_out, float* loss_out, voi
   a.loss_out = loss_out;
   a.normpart = h->normpart;
   a.error = h->dp_error;
-  a.timeout_cycles = 4000000000LL;       // ~2 s at 1.9 GHz: a missing peer fails instead of hanging the GPU
+  a.timeout_cycles = kDpTimeoutCycles;
   dp_allreduce_kernel<<<h->n_norm, RED_IDX, 0, (cudaStream_t)stream>>>(a);
   CU(cudaGetLastError());
   return 0;
@@ -1338,7 +1341,7 @@ int mafb200_train_step(mafb200_handle h, float* params, const float* x, const fl
       a.flags_of[r] = reinterpret_cast<unsigned int*>(h->dp_peer_sym[r] + 2 * sf);
     }
     a.error = h->dp_error;
-    a.timeout_cycles = 4000000000LL;
+    a.timeout_cycles = kDpTimeoutCycles;
     a.recv_off = (long long)dp_recv_off(Pk);
   }
   a.trace = h->trace ? h->trace + 900 : nullptr;

@@ -595,6 +595,9 @@ class TrainerModule:
             n += 1
         if pipe is not None:
             total += float(pipe.drain().sum())
+            if pipe.peer and self.model.engine().dp_error():
+                raise RuntimeError("data-parallel exchange timed out: a peer rank did not reach the step "
+                                   "(its process died or stalled for longer than the exchange time-out)")
         return {"train/loss": total / max(num_train_steps, 1), "epoch_time": time.time() - start_time}
 
     def eval_model(self, data_loader: Iterator, log_prefix: Optional[str] = "") -> Dict[str, Any]:
