@@ -455,3 +455,41 @@ def test_sass_shows_blackwell_native_paths():
     flow = [s for n, s in per_fn.items() if "maf_flow_kernel" in n]
     assert flow and all({"UBLKCP", "SYNCS", "FFMA2"} <= s for s in flow)
     assert not any("HMMA" in s for s in per_fn.values())
+
+
+def test_hmc_restatement_samples_the_right_distribution():
+    """The restated transition (leapfrog in the unconstrained space + Metropolis) targets prior x likelihood: a
+    Gaussian likelihood under a Uniform(-1, 2) prior and a Normal prior, moments against quadrature."""
+    from oracle import hmc_numpy
+    rng = np.random.default_rng(3)
+    n, C = 512, 2
+    mu, sig = np.array([0.6, -0.3]), np.array([0.8, 0.5])
+
+    def ll_grad(theta):
+        d = (theta - mu) / sig
+        return -0.5 * (d * d).sum(1), -d / sig
+
+    kind = np.array([1, 0]); lo = np.array([-1.0, 0.0]); hi = np.array([2.0, 1.0])   # U(-1, 2) x N(0, 1)
+    z = rng.normal(size=(n, C)) * 0.1
+    ld, g, th = hmc_numpy.log_density_and_grad(z, kind, lo, hi, ll_grad)
+    eps, im, keep = 0.25, np.ones(C), []
+    for it in range(160):
+        p = rng.normal(size=(n, C))
+        z1, p1, g1, ld1, th1 = hmc_numpy.leapfrog(z, p, g, eps, im, int(rng.integers(3, 9)), kind, lo, hi, ll_grad)
+        dh = (ld1 - 0.5 * (p1 ** 2).sum(1)) - (ld - 0.5 * (p ** 2).sum(1))
+        acc = np.log(rng.uniform(size=n)) < dh
+        z, g, ld, th = (np.where(acc[:, None], z1, z), np.where(acc[:, None], g1, g), np.where(acc, ld1, ld),
+                        np.where(acc[:, None], th1, th))
+        if it >= 60:
+            keep.append(th.copy())
+    s = np.concatenate(keep)
+    # dimension 0: N(0.6, 0.8^2) truncated to (-1, 2); dimension 1: N(-0.3, 0.5^2) x N(0, 1) = N(-0.24, 0.2)
+    t = np.linspace(-1, 2, 20001)
+    w = np.exp(-0.5 * ((t - mu[0]) / sig[0]) ** 2)
+    m0 = (t * w).sum() / w.sum()
+    v0 = ((t - m0) ** 2 * w).sum() / w.sum()
+    v1 = 1.0 / (1.0 / sig[1] ** 2 + 1.0)
+    m1 = v1 * mu[1] / sig[1] ** 2
+    assert s[:, 0].min() > -1 and s[:, 0].max() < 2
+    assert abs(s[:, 0].mean() - m0) < 0.03 and abs(s[:, 0].var() - v0) < 0.03
+    assert abs(s[:, 1].mean() - m1) < 0.02 and abs(s[:, 1].var() - v1) < 0.02
