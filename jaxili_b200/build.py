@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libmafb200.so")
 SOURCES = ["mafb200.cu"]
-HEADERS = ["plan.h", "common.cuh", "flow_kernel.cuh", "opt_kernels.cuh", "sample_kernel.cuh", "dp_kernel.cuh", "hmc_kernels.cuh", "wide_kernels.cuh", "wide_tc.cuh", "pipeline.inc",
+HEADERS = ["plan.h", "common.cuh", "flow_kernel.cuh", "chain_kernel.cuh", "opt_kernels.cuh", "sample_kernel.cuh", "dp_kernel.cuh", "hmc_kernels.cuh", "wide_kernels.cuh", "wide_tc.cuh", "pipeline.inc",
            os.path.join("..", "..", "include", "mafb200.h")]
 
 

@@ -44,6 +44,15 @@ struct FlowArgs {
     int nb_shift, nbg, nKG;   // column blocks per half-warp = 1<<nb_shift (<= 8), groups, row groups
     int bB;                   // weight gradient: warp blocks = nKG * nbg
   } ph[MAFB_MAX_LIN];
+  // chain kernel (chain_kernel.cuh): lane map of the row-owning warps per product.  A lane holds `groups` 4x4
+  // tiles of the warp's 4 rows and one of 1 << ks_shift parts of the reduction
+  struct ChainPh {
+    int ks_shift;             // 2: lane = part * 8 + column slot, 3: lane = part * 4 + column slot
+    int groups;               // column blocks per lane (1 or 2; 2 only with ks_shift == 2)
+    int n_pass;               // passes over the column blocks ((32 >> ks_shift) * groups per pass)
+    int nsteps;               // reduction steps per lane = padded reduction length >> ks_shift
+    int nCB;                  // column blocks
+  } cf[MAFB_MAX_LIN], cx[MAFB_MAX_LIN];   // forward product, input-gradient product
   long long* trace;           // debug: clock64 stamps of CTA 0 at phase boundaries (nullable)
 };
 
@@ -68,7 +77,7 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
   uint64_t* wbar = reinterpret_cast<uint64_t*>(smem_raw);   // [2] weight images
   uint64_t* sbar = wbar + 2;                                // [2] input tiles
   float* loss_acc = reinterpret_cast<float*>(smem_raw + 32);
-  float* sm = reinterpret_cast<float*>(smem_raw + 64);
+  float* sm = reinterpret_cast<float*>(smem_raw + MAFB_SMEM_HDR);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = NT / 32;

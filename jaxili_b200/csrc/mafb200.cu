@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "flow_kernel.cuh"
+#include "chain_kernel.cuh"
 #include "opt_kernels.cuh"
 #include "sample_kernel.cuh"
 #include "dp_kernel.cuh"
@@ -188,7 +189,13 @@ bool plan_layout(Plan& P, int R, bool stash_all, int n_wbuf, int limit) {
   o += maxhp * RP;
   P.o_g[1] = o;
   o += maxhp * RP;
-  P.smem_bytes = 64 + o * 4;
+  // chain kernel: one gradient buffer per linear (its gradient warps consume them asynchronously)
+  for (int i = 0; i < P.n_lin; ++i) {
+    if (i == P.n_lin - 1) P.o_gl[i] = P.o_obuf;
+    else if (i < 2) P.o_gl[i] = P.o_g[i];
+    else { P.o_gl[i] = o; o += P.lin[i].NP * RP; }
+  }
+  P.smem_bytes = MAFB_SMEM_HDR + o * 4;
   return P.smem_bytes <= limit;
 }
 
@@ -214,11 +221,11 @@ bool make_plan(const MafDesc& d, const int* dims, Plan& P, int occ) {
     ln.KP = r4(ln.K);
     ln.NP = r4(ln.N);
     ln.w_off = fo;
-    fo += ln.K * ln.NP;
+    fo += ln.KP * ln.NP;          // zero rows K..KP-1: the chain kernel's reduction loops run over KP
     ln.b_off = fo;
     fo += ln.NP;
     ln.wt_off = bo;
-    bo += ln.N * ln.KP;
+    bo += ln.NP * ln.KP;          // zero rows N..NP-1
     ln.pw_off = po;
     po += ln.K * ln.N;
     ln.pb_off = po;
@@ -331,9 +338,33 @@ static size_t dp_slot_floats(const Plan& P) { return (size_t)((P.P + 3) & ~3) + 
 static size_t dp_recv_off(const Plan& P) { return 2 * dp_slot_floats(P) + 8; }
 static size_t dp_total_floats(const Plan& P) { return dp_recv_off(P) + 2 * (2 * DP_MAX_WORLD * dp_slot_floats(P)); }
 
+// 0: chain kernel where it applies (default), 1: always the barrier-phased kernel (env MAFB200_FLOW=phased)
+static int flow_mode() {
+  static const int mode = [] { const char* e = getenv("MAFB200_FLOW"); return (e && strcmp(e, "phased") == 0) ? 1 : 0; }();
+  return mode;
+}
+// the chain kernel serves forward-only launches on every plan and the reverse pass when every layer's
+// activations are stashed; the conditioner-gradient mode stays on the barrier-phased kernel
+static bool use_chain(const Plan& P, const FlowArgs& A, bool bwd) {
+  if (flow_mode() == 1 || P.threads != kFlowThreads) return false;
+  if (bwd && (!P.stash_all || A.out_dy)) return false;
+  return P.n_lin <= 6;
+}
+
 template <bool BWD>
 static void launch_flow(const Plan& P, const FlowArgs& A, int grid, cudaStream_t st) {
   const bool relu = P.act == MAFB200_ACT_RELU;
+  if (use_chain(P, A, BWD)) {
+    constexpr int nt = BWD ? CH_NT_BWD : CH_NT_FWD;
+    if (P.n_lin == 3) {
+      if (relu) maf_chain_kernel<BWD, true, 3><<<grid, nt, P.smem_bytes, st>>>(P, A);
+      else maf_chain_kernel<BWD, false, 3><<<grid, nt, P.smem_bytes, st>>>(P, A);
+    } else {
+      if (relu) maf_chain_kernel<BWD, true, 0><<<grid, nt, P.smem_bytes, st>>>(P, A);
+      else maf_chain_kernel<BWD, false, 0><<<grid, nt, P.smem_bytes, st>>>(P, A);
+    }
+    return;
+  }
 #define LAUNCH(NT_, R_, L_) maf_flow_kernel<BWD, R_, NT_, L_><<<grid, NT_, P.smem_bytes, st>>>(P, A)
 #define PICK_L(NT_, R_) do { if (P.n_lin == 3) LAUNCH(NT_, R_, 3); else LAUNCH(NT_, R_, 0); } while (0)
   if (P.threads == kFlowThreads2) {
@@ -786,6 +817,11 @@ int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shi
     SET_FLOW(true, true, 3) SET_FLOW(true, false, 3) SET_FLOW(false, true, 3) SET_FLOW(false, false, 3)
     SET_FLOW(true, true, 0) SET_FLOW(true, false, 0) SET_FLOW(false, true, 0) SET_FLOW(false, false, 0)
 #undef SET_FLOW
+#define SET_CHAIN(B_, R_, L_) \
+  CUH(cudaFuncSetAttribute(maf_chain_kernel<B_, R_, L_>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    SET_CHAIN(true, true, 3) SET_CHAIN(true, false, 3) SET_CHAIN(false, true, 3) SET_CHAIN(false, false, 3)
+    SET_CHAIN(true, true, 0) SET_CHAIN(true, false, 0) SET_CHAIN(false, true, 0) SET_CHAIN(false, false, 0)
+#undef SET_CHAIN
   }
   if (have_sampler) {
     CUH(cudaFuncSetAttribute(maf_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->splan.smem_bytes));
@@ -1081,6 +1117,30 @@ static void fill_phases(const Plan& P, FlowArgs& A, bool want_dy = false, bool s
     const int kpw = 16 >> nbs;
     ph.nKG = (ph.nKB + kpw - 1) / kpw;
     ph.bB = skip_wgrad ? 0 : ph.nKG * ph.nbg;
+  }
+  // chain kernel: per product, the lane map that minimises passes x (FMA cycles + reduce/epilogue overhead)
+  auto pick = [](int nCB, int QP, bool pairs, FlowArgs::ChainPh& c) {
+    static const int cand[3][2] = {{2, 2}, {2, 1}, {3, 1}};   // {ks_shift, groups}
+    int best = -1, best_cost = 1 << 30;
+    for (int t = 0; t < 3; ++t) {
+      const int sh = cand[t][0], g = cand[t][1];
+      if (sh == 3 && (pairs || QP % 8)) continue;           // 8 parts: whole steps only, single columns
+      const int per_pass = (32 >> sh) * g;
+      const int passes = (nCB + per_pass - 1) / per_pass;
+      const int cost = passes * ((QP >> sh) * 16 * g + 40 + 14 * g + (sh == 3 ? 10 : 0));
+      if (cost < best_cost) { best_cost = cost; best = t; }
+    }
+    c.ks_shift = cand[best][0];
+    c.groups = cand[best][1];
+    const int per_pass = (32 >> c.ks_shift) * c.groups;
+    c.n_pass = (nCB + per_pass - 1) / per_pass;
+    c.nsteps = QP >> c.ks_shift;
+    c.nCB = nCB;
+  };
+  for (int i = 0; i < P.n_lin; ++i) {
+    const LinDesc& ln = P.lin[i];
+    pick(ln.NP / 4, ln.KP, i == P.n_lin - 1, A.cf[i]);              // last linear: (mu, logp) column pairs
+    pick((i == 0 ? P.DP : ln.KP) / 4, ln.NP, false, A.cx[i]);
   }
 }
 

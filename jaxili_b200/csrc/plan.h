@@ -5,15 +5,16 @@
 
 #define MAFB_MAX_LIN 6      // masked linears per MADE = n_hidden + 1
 #define MAFB_MAX_DEG 64     // n_in limit of the staircase sampler tables
+#define MAFB_SMEM_HDR 128   // bytes in front of the float layout: mbarriers, loss accumulators
 
 // One masked linear of the MADE (jaxili/model.py:517-544).  Feature counts are padded to
 // multiples of 4 so every shared-memory row can be read with 128-bit loads.
 struct LinDesc {
   int K, N;      // in, out
   int KP, NP;    // padded
-  int w_off;     // forward image: W[K][NP] (mask folded), floats from image start
+  int w_off;     // forward image: W[KP][NP] (mask folded, rows K..KP-1 zero), floats from image start
   int b_off;     // forward image: bias[NP]
-  int wt_off;    // backward image: Wt[N][KP], floats from backward-image start
+  int wt_off;    // backward image: Wt[NP][KP] (rows N..NP-1 zero), floats from backward-image start
   int pw_off;    // kernel offset inside one layer of the flat parameter vector
   int pb_off;    // bias offset inside one layer of the flat parameter vector
 };
@@ -45,7 +46,9 @@ struct Plan {
   int o_cst;                    // standardisation constants [2D + 2C]
   int o_red;                    // [32] per-warp loss contributions of the finalize step
   int o_gy;                     // [round4(C)][RP]: gradient w.r.t. the standardised conditioner (dy mode)
-  int o_g[2];                   // ping-pong [max HP][RP] hidden-gradient buffers
+  int o_g[2];                   // ping-pong [max HP][RP] hidden-gradient buffers (barrier-phased kernel)
+  int o_gl[MAFB_MAX_LIN];       // gradient w.r.t. the output of linear i, one buffer per linear (chain kernel);
+                                // o_gl[n_lin-1] == o_obuf, o_gl[0..1] alias o_g[0..1]
   int smem_bytes;
 };
 
