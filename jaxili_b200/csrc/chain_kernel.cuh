@@ -6,37 +6,53 @@
 // chain of 15 forward + 15 reverse dependent linears: a design that spreads every linear over the whole CTA pays
 // a CTA barrier, a pipeline fill and a drain per linear (47 % barrier stall in round 1).  Here
 //
-//   * CHAIN warps own rows.  Warp c holds rows 4c..4c+3 through every linear of every layer, forward and
-//     reverse: the only synchronisation on the dependent chain is __syncwarp.  Two chain warps per SM
-//     sub-partition, issued with priority (highest warp ids).  A lane holds 4 rows x 4 (or 8) columns and one of
-//     4 (or 8) parts of the reduction; packed FFMA2; operands prefetched through a 4-stage register ring; the
-//     parts are combined by a shuffle reduce-scatter that leaves every lane 2 columns x 2 rows for the epilogue.
-//   * GRADIENT warps compute the weight/bias gradients [A;1]^T G, the only product that crosses rows.  They
-//     consume the per-linear gradient buffers asynchronously (named barriers full[i] / empty[i]) and fill the
-//     issue slots the chain leaves empty; they never sit on the critical path.
+//   * CHAIN warps own rows.  Warp c holds rows 8c..8c+7 through every linear of every layer, forward and
+//     reverse: the only synchronisation on the dependent chain is __syncwarp.  One chain warp per SM
+//     sub-partition, issued with priority (highest warp ids).  A lane holds 8 rows x 4 columns and one of 2, 4 or
+//     8 parts of the reduction (32 accumulators, 3 loads per 16 packed FFMA2); operands are prefetched through a
+//     4-stage register ring; the parts are combined by a shuffle reduce-scatter.
+//   * GRADIENT warps compute the weight/bias gradients [A;1]^T G, the only product that crosses rows: once per
+//     layer, all linears of the layer as one flat list of 8x4 tiles (one tile per lane, reduction over all rows
+//     of the tile, no cross-lane step).  They consume the gradient buffers asynchronously (two buffer sets,
+//     named barriers full[b] / empty[b]) and fill the issue slots the chain leaves empty.
 //   * one PRODUCER warp streams the weight images and the input tiles with bulk copies (TMA 1-D) behind
 //     full/empty mbarriers.
+// Everything is sized to keep the instruction stream FFMA2-dominated: round 1's kernel and the first versions of
+// this one issued 3-4 bookkeeping instructions per FFMA2 (ncu: 23-27 % FFMA2) and were issue/latency bound.
 #pragma once
 #include "common.cuh"
 #include "flow_kernel.cuh"
 
 namespace mafb {
 
-constexpr int CH_CW = 8;                         // chain warps: 4 rows each, 32-row tiles
-constexpr int CH_GW = 7;                         // gradient warps (16 warps per CTA: 128 registers per thread)
+constexpr int CH_CW = 4;                         // chain warps: 8 rows each, 32-row tiles
+constexpr int CH_GW = 7;                         // gradient warps
 constexpr int CH_NT_BWD = 32 * (1 + CH_GW + CH_CW);
 constexpr int CH_NT_FWD = 32 * (1 + CH_CW);
-constexpr int CH_MAX_LIN = 6;
-constexpr int CH_BAR_FULL = 1;                   // named barriers: full[i] = 1 + i, empty[i] = 7 + i
-constexpr int CH_BAR_EMPTY = 7;
-constexpr int CH_BAR_TILE = 13;                  // gradient warps are done with the tile's stash
-constexpr int CH_BAR_CHAIN = 14;                 // chain warps only (loss hand-off at the end)
+constexpr int CH_BAR_FULL = 1;                   // named barriers: full[b] = 1 + b, empty[b] = 3 + b
+constexpr int CH_BAR_EMPTY = 3;
+constexpr int CH_BAR_TILE = 5;                   // gradient warps are done with the tile's stash
+constexpr int CH_BAR_CHAIN = 6;                  // chain warps only (loss hand-off at the end)
 
 __device__ __forceinline__ void nbar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 __device__ __forceinline__ void nbar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// producer-side wait: poll with a back-off so the spin does not eat issue slots of the sub-partition it shares
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(256);
+  }
 }
 
 // acc[j][i] += a[i] * w[j]: 8 packed FFMA2 (row pairs, the weight as the broadcast operand)
@@ -47,158 +63,158 @@ __device__ __forceinline__ void ch_fma_tile(float (&acc)[4][4], const float (&a)
     for (int i = 0; i < 4; i += 2) ffma2(acc[j][i], acc[j][i + 1], a[i], a[i + 1], w[j], w[j]);
 }
 
-// n reduction steps of G 4x4 tiles that share the row operand; pa / pw advance by da / dw floats per step.
-// n % 4 steps are peeled off the front; the rest runs through a 4-stage register ring: the loads of step s+4 are
-// issued behind the FMAs of step s, i.e. 3 steps (>= 48 FMA-pipe cycles) ahead of their use -- more than the
-// 29-cycle shared-memory latency.
-template <int G>
-__device__ __forceinline__ void ch_mac(float (&acc)[G][4][4], const float* __restrict__ pa,
-                                       const float* const (&pw0)[G], int n, int da, int dw) {
-  const float* pw[G];
-#pragma unroll
-  for (int g = 0; g < G; ++g) pw[g] = pw0[g];
+// n reduction steps of the lane's 8x4 tile (two 4x4 tiles sharing the weight operand); pa / pw advance by da / dw
+// floats per step.  Operands run through a 4-stage register ring: the loads of step s+4 are issued behind the FMAs
+// of step s, i.e. 3 steps (96 FMA-pipe cycles) ahead of their use.
+__device__ __forceinline__ void ch_mac(float (&acc)[2][4][4], const float* __restrict__ pa,
+                                       const float* __restrict__ pw, int n, int da, int dw) {
   const int rem = n & 3;
 #pragma unroll 1
   for (int u = 0; u < rem; ++u) {
-    float a[4], w[G][4];
-    ldv(a, pa);
-#pragma unroll
-    for (int g = 0; g < G; ++g) ldv(w[g], pw[g]);
-#pragma unroll
-    for (int g = 0; g < G; ++g) ch_fma_tile(acc[g], a, w[g]);
+    float a0[4], a1[4], w[4];
+    ldv(a0, pa);
+    ldv(a1, pa + 4);
+    ldv(w, pw);
+    ch_fma_tile(acc[0], a0, w);
+    ch_fma_tile(acc[1], a1, w);
     pa += da;
-#pragma unroll
-    for (int g = 0; g < G; ++g) pw[g] += dw;
+    pw += dw;
   }
   int m = n - rem;                 // multiple of 4
   if (m == 0) return;
-  float a[4][4], w[4][G][4];
+  float a0[4][4], a1[4][4], w[4][4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    ldv(a[u], pa + u * da);
-#pragma unroll
-    for (int g = 0; g < G; ++g) ldv(w[u][g], pw[g] + u * dw);
+    ldv(a0[u], pa + u * da);
+    ldv(a1[u], pa + u * da + 4);
+    ldv(w[u], pw + u * dw);
   }
 #pragma unroll 1
   for (m -= 4; m > 0; m -= 4) {
     pa += 4 * da;
-#pragma unroll
-    for (int g = 0; g < G; ++g) pw[g] += 4 * dw;
+    pw += 4 * dw;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-#pragma unroll
-      for (int g = 0; g < G; ++g) ch_fma_tile(acc[g], a[u], w[u][g]);
-      ldv(a[u], pa + u * da);
-#pragma unroll
-      for (int g = 0; g < G; ++g) ldv(w[u][g], pw[g] + u * dw);
+      ch_fma_tile(acc[0], a0[u], w[u]);
+      ch_fma_tile(acc[1], a1[u], w[u]);
+      ldv(a0[u], pa + u * da);
+      ldv(a1[u], pa + u * da + 4);
+      ldv(w[u], pw + u * dw);
     }
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
-#pragma unroll
-    for (int g = 0; g < G; ++g) ch_fma_tile(acc[g], a[u], w[u][g]);
+  for (int u = 0; u < 4; ++u) {
+    ch_fma_tile(acc[0], a0[u], w[u]);
+    ch_fma_tile(acc[1], a1[u], w[u]);
+  }
 }
 
-// Reduce-scatter of a 4x4 tile (acc[col][row]) over the lanes that hold its reduction parts.
-// stage 1 (lane bit 4): keep column pair b1;  stage 2 (lane bit 3): keep row pair b0.
-__device__ __forceinline__ void ch_rs_2x2(const float (&acc)[4][4], bool b1, bool b0, float (&r)[2][2]) {
-  float t[2][4];
+// Reduce-scatter stages of a 4x4 tile (acc[col][row]) over the lanes that hold its reduction parts:
+// stage 1 (partner lane ^ 16) keeps column pair hi1, stage 2 (lane ^ 8) row pair hi0, stage 3 (lane ^ 4) one column.
+__device__ __forceinline__ void ch_rs_cols(const float (&acc)[4][4], bool hi, float (&t)[2][4]) {
 #pragma unroll
   for (int c = 0; c < 2; ++c)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float send = b1 ? acc[c][i] : acc[2 + c][i];
-      const float mine = b1 ? acc[2 + c][i] : acc[c][i];
+      const float send = hi ? acc[c][i] : acc[2 + c][i];
+      const float mine = hi ? acc[2 + c][i] : acc[c][i];
       t[c][i] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
     }
+}
+__device__ __forceinline__ void ch_rs_rows(const float (&t)[2][4], bool hi, float (&r)[2][2]) {
 #pragma unroll
   for (int c = 0; c < 2; ++c)
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const float send = b0 ? t[c][i] : t[c][2 + i];
-      const float mine = b0 ? t[c][2 + i] : t[c][i];
+      const float send = hi ? t[c][i] : t[c][2 + i];
+      const float mine = hi ? t[c][2 + i] : t[c][i];
       r[c][i] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
     }
 }
 
-// One product of the chain for the warp's 4 rows: out[c][r] = sum_q in[q][r] * W[q][c], all column blocks.
-//   KS = 4: lane = kq * 8 + cbl, the lane's reduction part is q = kq, kq+4, ...; G column blocks per lane
-//           (cbl and cbl + 8).  After the reduce-scatter a lane owns columns (ce, ce+1) x rows (re, re+1):
-//           epi(ce, re, v) with v[col][row].
-//   KS = 8: lane = kq * 4 + cbl, G = 1; a third stage (lane bit 2) leaves one column: epi(c, re, v) uses v[0][*].
-struct NoStamp { __device__ __forceinline__ void operator()(int) const {} };
-template <int KS, int G, class Epi, class St = NoStamp>
+// One product of the chain for the warp's 8 rows: out[c][r] = sum_q in[q][r] * W[q][c], all column blocks.
+// lane = kq * (32 >> ks_shift) + column slot; the lane's reduction part is q = kq, kq + KS, ... (KS = 2 or 4).
+//   KS = 2: the lane ends with columns (ce, ce+1) x 4 rows per row block:  epi(ce, rr, v) with v[2 cols][4 rows]
+//   KS = 4: columns (ce, ce+1) x 2 rows per row block:                     epi(ce, rr, v) with v[2][2]
+// rr = first row (relative to the warp's 8 rows).  KS is a run-time value on purpose: the kernel holds ONE copy
+// of this code for all products of the chain (instruction-cache footprint).
+template <class Epi>
 __device__ __forceinline__ void chain_gemm(const float* __restrict__ in, int RP, const float* __restrict__ W, int ldw,
-                                           int nCB, int nsteps, int n_pass, int lane, Epi&& epi, St&& st = St()) {
-  static_assert((KS == 4 && (G == 1 || G == 2)) || (KS == 8 && G == 1), "supported lane maps");
-  constexpr int CPL = 32 / KS;
-  const int cbl = lane & (CPL - 1);
-  const int kq = lane / CPL;
+                                           const FlowArgs::ChainPh& ph, int lane, Epi&& epi) {
+  const int ks_shift = ph.ks_shift, nCB = ph.nCB, nsteps = ph.nsteps, n_pass = ph.n_pass;
+  const int cpl = 32 >> ks_shift;
+  const int cbl = lane & (cpl - 1);
+  const int kq = lane >> (5 - ks_shift);
   const bool b1 = (lane & 16) != 0, b0 = (lane & 8) != 0;
+  const float* pin = in + kq * RP;
+  const float* pW = W + kq * ldw;
+  const int da = RP << ks_shift, dw = ldw << ks_shift;
 #pragma unroll 1
   for (int pass = 0; pass < n_pass; ++pass) {
-    float acc[G][4][4];
-    const float* pw[G];
-    bool ok[G];
+    float acc[2][4][4];
+    const int cb = pass * cpl + cbl;
+    const bool ok = cb < nCB;
+    const int c0 = 4 * (ok ? cb : nCB - 1);
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int cb = (pass * G + g) * CPL + cbl;
-      ok[g] = cb < nCB;
-      pw[g] = W + kq * ldw + 4 * (ok[g] ? cb : nCB - 1);
+    for (int g = 0; g < 2; ++g)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[g][j][i] = 0.f;
-    }
-    st(1);
-    ch_mac<G>(acc, in + kq * RP, pw, nsteps, KS * RP, KS * ldw);
-    st(2);
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int c0 = 4 * ((pass * G + g) * CPL + cbl);
-      float r[2][2];
-      ch_rs_2x2(acc[g], b1, b0, r);
-      st(3 + g);
-      if (KS == 4) {
-        if (ok[g]) epi(c0 + (b1 ? 2 : 0), b0 ? 2 : 0, r);
-      } else {
-        const bool b2 = (lane & 4) != 0;   // stage 3: keep column b2 of the pair
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const float send = b2 ? r[0][i] : r[1][i];
-          const float mine = b2 ? r[1][i] : r[0][i];
-          r[0][i] = mine + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-        if (ok[g]) epi(c0 + (b1 ? 2 : 0) + (b2 ? 1 : 0), b0 ? 2 : 0, r);
+    ch_mac(acc, pin, pW + c0, nsteps, da, dw);
+    const int ce = c0 + (b1 ? 2 : 0);
+    float t[2][2][4];
+    ch_rs_cols(acc[0], b1, t[0]);
+    ch_rs_cols(acc[1], b1, t[1]);
+    if (ks_shift == 1) {
+      if (ok) {
+        epi(ce, 0, t[0]);
+        epi(ce, 4, t[1]);
+      }
+    } else {
+      float r[2][2][2];
+      ch_rs_rows(t[0], b0, r[0]);
+      ch_rs_rows(t[1], b0, r[1]);
+      if (ok) {
+        epi(ce, b0 ? 2 : 0, r[0]);
+        epi(ce, b0 ? 6 : 4, r[1]);
       }
     }
   }
 }
 
-// dispatch on the host-chosen lane map; epi1(c, re, v[2 rows]) is called once per finished column
-template <class Epi, class St = NoStamp>
-__device__ __forceinline__ void chain_gemm_cols(const float* __restrict__ in, int RP, const float* __restrict__ W,
-                                                int ldw, const FlowArgs::ChainPh& ph, int lane, Epi&& epi1, St&& st = St()) {
-  auto both = [&](int ce, int re, const float (&v)[2][2]) {
-    epi1(ce, re, v[0]);
-    epi1(ce + 1, re, v[1]);
-  };
-  auto one = [&](int c, int re, const float (&v)[2][2]) { epi1(c, re, v[0]); };
-  if (ph.ks_shift == 3) chain_gemm<8, 1>(in, RP, W, ldw, ph.nCB, ph.nsteps, ph.n_pass, lane, one);
-  else if (ph.groups == 2) chain_gemm<4, 2>(in, RP, W, ldw, ph.nCB, ph.nsteps, ph.n_pass, lane, both, st);
-  else chain_gemm<4, 1>(in, RP, W, ldw, ph.nCB, ph.nsteps, ph.n_pass, lane, both, st);
-}
-// KS = 4 only: epi(ce, re, v[2 cols][2 rows]) gets the aligned column pair (ce even)
-template <class Epi>
-__device__ __forceinline__ void chain_gemm_pairs(const float* __restrict__ in, int RP, const float* __restrict__ W,
-                                                 int ldw, const FlowArgs::ChainPh& ph, int lane, Epi&& epi) {
-  if (ph.groups == 2) chain_gemm<4, 2>(in, RP, W, ldw, ph.nCB, ph.nsteps, ph.n_pass, lane, epi);
-  else chain_gemm<4, 1>(in, RP, W, ldw, ph.nCB, ph.nsteps, ph.n_pass, lane, epi);
+// Weight + bias gradient tile of one lane: out[i][j] = sum_r A[i * a_stride][r] * G[j * g_stride][r] over the
+// tile's rows, i < 8, j < 4.  Packed FFMA2 over the row pairs (t, t+1): even rows accumulate in acc, odd rows in
+// acc_odd.  A's feature rows continue into the ones row right behind the last feature, which makes the last
+// row of the product the bias gradient.
+__device__ __forceinline__ void dw_tile(const float* __restrict__ A, int a_stride, const float* __restrict__ G,
+                                        int g_stride, int Rt, float (&out)[8][4]) {
+  float acc_odd[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { out[i][j] = 0.f; acc_odd[i][j] = 0.f; }
+#pragma unroll 1
+  for (int r = 0; r < Rt; r += 4) {
+    float av[8][4], gv[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ldv(gv[j], G + j * g_stride + r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ldv(av[i], A + i * a_stride + r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int t = 0; t < 4; t += 2) ffma2(out[i][j], acc_odd[i][j], av[i][t], av[i][t + 1], gv[j][t], gv[j][t + 1]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[i][j] += acc_odd[i][j];
 }
 
-// NLIN > 0 fixes the number of masked linears per MADE at compile time (the loops over them unroll and the
-// per-linear descriptors become constant-bank operands); NLIN == 0 reads it from the plan.
-template <bool BWD, bool RELU, int NLIN>
+template <bool BWD, bool RELU>
 __global__ void __launch_bounds__(BWD ? CH_NT_BWD : CH_NT_FWD, 1)
 maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -212,11 +228,10 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
   constexpr int NT = BWD ? CH_NT_BWD : CH_NT_FWD;
   constexpr int GW = BWD ? CH_GW : 0;
   constexpr int NB = 32 * (GW + CH_CW);                      // threads on the full / empty / tile barriers
-  constexpr int UL = NLIN > 0 ? NLIN : 1;                    // unroll factor of the loops over the linears
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = P.D, C = P.C, L = P.L, RP = P.RP;
-  const int n_lin = NLIN > 0 ? NLIN : P.n_lin;
-  const int Rt = A.Rt, nRB = Rt / 4;
+  const int n_lin = P.n_lin;
+  const int Rt = A.Rt;
   const long long row_base = A.batch_index ? (long long)(A.batch_index[0] % A.n_batches) * A.B : 0;
   const int grid = gridDim.x;
   const int my_n = (A.n_tiles - (int)blockIdx.x + grid - 1) / grid;
@@ -263,12 +278,13 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
   float* const cst = sm + P.o_cst;   // [shift D][inv_scale D][mean C][std C]
   for (int idx = tid; idx < 2 * D + 2 * C; idx += NT) cst[idx] = A.stdc[idx];
   if (BWD) {
-    // a feature row of ones behind every weight-gradient A operand: [A;1]^T G yields the bias gradient
+    // a feature row of ones right behind the last feature of every weight-gradient A operand (row K; it meets a
+    // zero row of the weight image in the forward products): [A;1]^T G yields the bias gradient as row K
     for (int idx = tid; idx < RP; idx += NT) {
       for (int l = 0; l < L; ++l) {
-        sm[P.o_xin + l * P.xin_stride + P.lin[0].KP * RP + idx] = 1.f;
+        sm[P.o_xin + l * P.xin_stride + P.lin[0].K * RP + idx] = 1.f;
         for (int i = 1; i < n_lin; ++i)
-          sm[P.o_slot + l * P.slot_stride + P.h_off[i] + P.lin[i].KP * RP + idx] = 1.f;
+          sm[P.o_slot + l * P.slot_stride + P.h_off[i] + P.lin[i].K * RP + idx] = 1.f;
       }
     }
   }
@@ -307,7 +323,7 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
       const int buf = two_wbuf ? (s & 1) : 0;
       const int use = two_wbuf ? (s >> 1) : s;         // earlier fills of this buffer
       if (lane == 0) {
-        if (use > 0) mbar_wait(&wempty[buf], (uint32_t)((use - 1) & 1));
+        if (use > 0) mbar_wait_sleep(&wempty[buf], (uint32_t)((use - 1) & 1));
         int layer, part;
         if (!BWD || j < L) { layer = j; part = 0; } else { layer = 2 * L - 1 - j; part = 1; }
         const float* src = A.wimg + (size_t)layer * P.img_floats;
@@ -319,7 +335,7 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
       }
       if (j == jstage && ti + 2 < my_n) {
         // tile ti has been transposed out of its staging buffer (its first weight request was released)
-        if (lane == 0) mbar_wait(&sempty[ti & 1], (uint32_t)((ti >> 1) & 1));
+        if (lane == 0) mbar_wait_sleep(&sempty[ti & 1], (uint32_t)((ti >> 1) & 1));
         __syncwarp();
         stage_issue(ti + 2);
       }
@@ -329,40 +345,72 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
   }
 
   // ======================================================================== gradient warps
+  // layer step sq = ti * L + (L - 1 - k) alternates between the two gradient-buffer sets
   if (BWD && warp <= GW) {
     const int gw = warp - 1;
     float* pg_cta = A.partial_grad + (size_t)blockIdx.x * P.P;
+    const int total_steps = my_n * L;
+    // flat list of 8x4 tiles over the linears of one layer, one tile per lane and round; a tile takes the strided
+    // features k = kb + i * nKB (i < 8; k == K is the ones row = bias), n = nb + j * nNB (j < 4): the rows one
+    // warp instruction reads are consecutive features, which the pitch maps to distinct banks
+    int n_tiles_layer = 0;
+#pragma unroll 1
+    for (int i = 0; i < n_lin; ++i) n_tiles_layer += ((P.lin[i].K + 8) >> 3) * (P.lin[i].NP >> 2);
+    int sq = 0;
     for (int ti = 0; ti < my_n; ++ti) {
       const bool accum = ti > 0;
-      const bool last_tile = ti + 1 == my_n;
-      for (int k = L - 1; k >= 0; --k) {
+      for (int k = L - 1; k >= 0; --k, ++sq) {
         float* pg = pg_cta + (size_t)k * P.ppl;
-        const float* xin = sm + P.o_xin + k * P.xin_stride;
-        const float* slot = sm + P.o_slot + k * P.slot_stride;
-#pragma unroll UL
-        for (int ii = 0; ii < n_lin; ++ii) {
-          const int i = n_lin - 1 - ii;
-          const LinDesc& ln = P.lin[i];
-          const FlowArgs::Phase& ph = A.ph[i];
-          const float* G = sm + P.o_gl[i];
-          const float* Ain = (i == 0) ? xin : slot + P.h_off[i];
-          nbar_sync(CH_BAR_FULL + i, NB);
-          stamp(500 + 10 * k + i);
-          for (int blk = gw; blk < ph.bB; blk += GW) {
-            int b = blk, g = 0;
-            while (b >= ph.nKG) { b -= ph.nKG; ++g; }
-            const int l16 = lane & 15;
-            const int kb = b * (16 >> ph.nb_shift) + (l16 >> ph.nb_shift);
-            const int nb = (g << ph.nb_shift) + (l16 & ((1 << ph.nb_shift) - 1));
-            mm_inner_rs2(Ain, ln.K, ln.KP, G, ln.N, Rt, RP, kb, ph.nKB, nb < ph.nNB ? nb : ph.nNB - 1, ph.nNB,
-                         lane >> 4, nb < ph.nNB && kb < ph.nKB, pg + ln.pw_off, accum);
-            if (k == 3) stamp(800 + i);
+        const float* gset = sm + P.o_gb + (sq & 1) * P.gb_stride;
+        nbar_sync(CH_BAR_FULL + (sq & 1), NB);
+        stamp(500 + 10 * k);
+        for (int g0 = gw * 32; g0 < n_tiles_layer; g0 += GW * 32) {
+          int g = g0 + lane;
+          const bool active = g < n_tiles_layer;
+          if (!active) g = 0;
+          // which linear, which tile
+          int li = 0, nKB = 1, nNB = 1, local = 0, base = 0;
+#pragma unroll 1
+          for (int i = 0; i < n_lin; ++i) {
+            const int kbs = (P.lin[i].K + 8) >> 3, nbs = P.lin[i].NP >> 2;
+            if (g >= base && g < base + kbs * nbs) { li = i; nKB = kbs; nNB = nbs; local = g - base; }
+            base += kbs * nbs;
           }
-          stamp(600 + 10 * k + i);
-          if (!(last_tile && k == 0)) nbar_arrive(CH_BAR_EMPTY + i, NB);
+          g = local;
+          const int kb = g / nNB, nb = g - kb * nNB;
+          int K = 0, N = 0, pw_off = 0, goff = 0, aoff = 0;
+#pragma unroll 1
+          for (int i = 0; i < n_lin; ++i)
+            if (i == li) {
+              K = P.lin[i].K; N = P.lin[i].N; pw_off = P.lin[i].pw_off; goff = P.g_off[i];
+              aoff = i == 0 ? P.o_xin + k * P.xin_stride : P.o_slot + k * P.slot_stride + P.h_off[i];
+            }
+          float out[8][4];
+          dw_tile(sm + aoff + kb * RP, nKB * RP, gset + goff + nb * RP, nNB * RP, Rt, out);
+          if (active) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int kk = kb + i * nKB;
+              if (kk <= K) {
+                float* prow = pg + pw_off + kk * N;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int n = nb + j * nNB;
+                  if (n < N) {
+                    // this thread is the only writer of its entries of the CTA's partial-gradient slice; later
+                    // tiles add with a fire-and-forget reduction (no load latency, same order each run)
+                    if (accum) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(prow + n), "f"(out[i][j]) : "memory");
+                    else prow[n] = out[i][j];
+                  }
+                }
+              }
+            }
+          }
         }
+        stamp(600 + 10 * k);
+        if (sq + 2 < total_steps) nbar_arrive(CH_BAR_EMPTY + (sq & 1), NB);
       }
-      if (!last_tile) nbar_arrive(CH_BAR_TILE, NB);
+      if (ti + 1 < my_n) nbar_arrive(CH_BAR_TILE, NB);
     }
     stamp_end();
     return;
@@ -370,14 +418,16 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
 
   // ======================================================================== chain warps
   const int cw = warp - GW - 1;
-  const bool has_rows = cw < nRB;
-  const int r0 = 4 * (has_rows ? cw : 0);
-  float* const obuf = sm + P.o_obuf;
+  const int nRB = Rt / 4;
+  const bool has_rows = 2 * cw < nRB;
+  const bool rb1 = 2 * cw + 1 < nRB;                  // the warp's second row block exists in the tile
+  const int r0 = 8 * (has_rows ? cw : 0);
   float* const gu = sm + P.o_gu;
   float* const gx = sm + P.o_gx;
   float* const ld = sm + P.o_ld;
   float my_loss = 0.f;
-  int req = 0;
+  int req = 0, sq = 0;
+  const int total_steps = my_n * L;
 
   auto w_acquire = [&](int s) -> const float* {
     const int buf = two_wbuf ? (s & 1) : 0;
@@ -389,6 +439,8 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
     __syncwarp();
     if (lane == 0) mbar_arrive(&wempty[two_wbuf ? (s & 1) : 0]);
   };
+  // rows rr .. rr+NR-1 of the warp (relative) exist in the tile?  (a row block is all or nothing)
+  auto rows_ok = [&](int rr) { return rr < 4 || rb1; };
 
   for (int ti = 0; ti < my_n; ++ti) {
     const int t = blockIdx.x + ti * grid;
@@ -405,201 +457,239 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
     if (has_rows) {
       const float* st = sm + P.o_stage + (ti & 1) * P.stage_stride;
       float* xin0 = sm + P.o_xin;
-      const int r = r0 + (lane & 3);
-      const bool ok = r < valid;
-      for (int j = lane >> 2; j < D + C; j += 8) {
-        if (j < D) {
-          // distrax.ScalarAffine.inverse: (x - shift) * (1/scale)
-          xin0[j * RP + r] = ok ? (st[r * D + j] - cst[j]) * cst[D + j] : 0.f;
-          ld[j * RP + r] = 0.f;
-        } else {
-          // Standardizer: (y - mean) / std
-          const int c = j - D;
-          const float v = ok ? __fdiv_rn(st[P.R * D + r * C + c] - cst[2 * D + c], cst[2 * D + C + c]) : 0.f;
-          for (int l = 0; l < L; ++l) sm[P.o_xin + l * P.xin_stride + j * RP + r] = v;
+      const int r = r0 + (lane & 7);
+      if (r < Rt) {
+        const bool ok = r < valid;
+        for (int j = lane >> 3; j < D + C; j += 4) {
+          if (j < D) {
+            // distrax.ScalarAffine.inverse: (x - shift) * (1/scale)
+            xin0[j * RP + r] = ok ? (st[r * D + j] - cst[j]) * cst[D + j] : 0.f;
+            ld[j * RP + r] = 0.f;
+          } else {
+            // Standardizer: (y - mean) / std
+            const int c = j - D;
+            const float v = ok ? __fdiv_rn(st[P.R * D + r * C + c] - cst[2 * D + c], cst[2 * D + C + c]) : 0.f;
+            for (int l = 0; l < L; ++l) sm[P.o_xin + l * P.xin_stride + j * RP + r] = v;
+          }
         }
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sempty[ti & 1]);
-
-    // ---- forward through the L MAF layers
     stamp(3);
-    for (int k = 0; k < L; ++k) {
-      const float* wf = w_acquire(req);
-      stamp(90 + k);
-      if (has_rows) {
-        float* slot = sm + P.o_slot + (BWD ? k : 0) * P.slot_stride;
-        const float* xin_k = sm + P.o_xin + k * P.xin_stride;
-        float* xnext = (k + 1 < L) ? sm + P.o_xin + (k + 1) * P.xin_stride : gu;
-        const float* in = xin_k + r0;
-#pragma unroll UL
-        for (int i = 0; i < n_lin; ++i) {
-          const LinDesc& ln = P.lin[i];
-          const float* W = wf + ln.w_off;
-          const float* bias = wf + ln.b_off;
-          if (i < n_lin - 1) {
-            float* hout = slot + P.h_off[i + 1] + r0;
-            float* dout = slot + P.d_off[i + 1] + r0;
-            chain_gemm_cols(in, RP, W, ln.NP, A.cf[i], lane, [&](int c, int re, const float (&v)[2]) {
-              const float bj = bias[c];
-              float hv[2], dv[2];
-#pragma unroll
-              for (int q = 0; q < 2; ++q) act_eval<RELU>(P.act, v[q] + bj, hv[q], dv[q]);
-              stv(hout + c * RP + re, hv);
-              if (!RELU && BWD) stv(dout + c * RP + re, dv);
-            }, [&](int id) { if (k == 1) stamp(700 + 10 * i + id); });
-            in = hout;
-          } else {
-            // the last linear's image interleaves (mu_j, logp_j): a lane ends with both for 2 rows; the affine
-            // autoregressive transform (jaxili/model.py:739-742) runs right here
-            float* sbuf = slot + P.s_off + r0;
-            float* vbuf = slot + P.v_off + r0;
-            chain_gemm_pairs(in, RP, W, ln.NP, A.cf[i], lane, [&](int ce, int re, const float (&v)[2][2]) {
-              const int j = ce >> 1;
-              if (j < D) {
-                float bb[2], xv[2], sv[2], vv[2], lv[2];
-                ldv(bb, bias + ce);
-                ldv(xv, xin_k + r0 + j * RP + re);
-                ldv(lv, ld + r0 + j * RP + re);
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                  const float lp = v[1][q] + bb[1];
-                  sv[q] = expf(0.5f * lp);
-                  vv[q] = (xv[q] - (v[0][q] + bb[0])) * sv[q];
-                  lv[q] += 0.5f * lp;
-                }
-                if (BWD) {
-                  stv(sbuf + j * RP + re, sv);
-                  stv(vbuf + j * RP + re, vv);
-                }
-                stv(ld + r0 + j * RP + re, lv);
-                const int jj = P.reverse ? D - 1 - j : j;
-                stv(xnext + r0 + jj * RP + re, vv);
+
+    // ---- the chain as ONE rolled loop over its products: forward (k up, i up), the per-row finalize step, reverse
+    //      (k down, i down).  One copy of the product code serves them all; the epilogue is selected per product.
+    const int n_fwd = L * n_lin;
+    const int n_items = BWD ? 2 * n_fwd + 1 : n_fwd + 1;
+    int k = 0, i = 0;                // current layer / linear
+    bool rev = false;
+    const float* wbuf_cur = nullptr;
+#pragma unroll 1
+    for (int it = 0; it < n_items; ++it) {
+      if (it == n_fwd) {
+        // ---- log-probability per row (jaxili/model.py:919-921 + 1094-1098); seed of the reverse pass.
+        //      4 lanes per row stride the features; the last layer's elementwise reverse step is done here.
+        float* gset = sm + P.o_gb + (sq & 1) * P.gb_stride;          // gradient-buffer set of the coming layer step
+        if (BWD && sq >= 2) nbar_sync(CH_BAR_EMPTY + (sq & 1), NB);  // its previous content has been consumed
+        if (has_rows) {
+          const int r = r0 + (lane >> 2);
+          const int f0 = lane & 3;
+          const bool rok = r < Rt, vok = r < valid;
+          const float* pslot = sm + P.o_slot + (BWD ? L - 1 : 0) * P.slot_stride;
+          float* gx_l = gx + ((L - 1) & 1) * P.DP * RP;
+          float acc = 0.f, ldsum = 0.f;
+          if (rok)
+            for (int j = f0; j < D; j += 4) {
+              const float u = gu[j * RP + r];
+              const float l = ld[j * RP + r];
+              ldsum += l;
+              acc += l - 0.5f * u * u;
+              if (BWD) {
+                const float gv = vok ? u * A.inv_b : 0.f;
+                const int jm = P.reverse ? D - 1 - j : j;    // output j of the flow is MADE feature jm of the last layer
+                const float s = pslot[P.s_off + jm * RP + r], v = pslot[P.v_off + jm * RP + r];
+                gset[jm * RP + r] = vok ? -gv * s : 0.f;
+                gset[(D + jm) * RP + r] = vok ? 0.5f * gv * v - 0.5f * A.inv_b : 0.f;
+                gx_l[jm * RP + r] = vok ? gv * s : 0.f;
               }
-            });
+            }
+#pragma unroll
+          for (int o = 1; o < 4; o <<= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            ldsum += __shfl_xor_sync(0xffffffffu, ldsum, o);
           }
-          __syncwarp();
-          stamp(100 + 10 * k + i);
-        }
-      }
-      w_release(req);
-      ++req;
-    }
-
-    // ---- log-probability per row (jaxili/model.py:919-921 + 1094-1098); seed of the reverse pass.
-    //      8 lanes per row stride the features; the last layer's elementwise reverse step is done here.
-    if (BWD && ti > 0) nbar_sync(CH_BAR_EMPTY + n_lin - 1, NB);   // obuf: previous content consumed
-    if (has_rows) {
-      const int r = r0 + (lane >> 3);
-      const int f0 = lane & 7;
-      const bool vok = r < valid;
-      const float* pslot = sm + P.o_slot + (BWD ? L - 1 : 0) * P.slot_stride;
-      float* gx_l = gx + ((L - 1) & 1) * P.DP * RP;
-      float acc = 0.f, ldsum = 0.f;
-      for (int j = f0; j < D; j += 8) {
-        const float u = gu[j * RP + r];
-        const float l = ld[j * RP + r];
-        ldsum += l;
-        acc += l - 0.5f * u * u;
-        if (BWD) {
-          const float gv = vok ? u * A.inv_b : 0.f;
-          const int jm = P.reverse ? D - 1 - j : j;      // output j of the flow is MADE feature jm of the last layer
-          const float s = pslot[P.s_off + jm * RP + r], v = pslot[P.v_off + jm * RP + r];
-          obuf[jm * RP + r] = vok ? -gv * s : 0.f;
-          obuf[(D + jm) * RP + r] = vok ? 0.5f * gv * v - 0.5f * A.inv_b : 0.f;
-          gx_l[jm * RP + r] = vok ? gv * s : 0.f;
-        }
-      }
-#pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {
-        acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        ldsum += __shfl_xor_sync(0xffffffffu, ldsum, o);
-      }
-      const float lp = acc - (float)D * kHalfLog2Pi + A.logdet_const;
-      const bool lead = f0 == 0 && vok;
-      if (lead && A.out_logp) A.out_logp[row0 + r] = lp;
-      if (!BWD && lead && A.out_logdet) A.out_logdet[row0 + r] = ldsum;
-      if (BWD) my_loss += warp_sum(lead ? -lp * A.inv_b : 0.f);
-      if (!BWD && A.out_u) {   // own rows are contiguous in HBM
-        const int nrow = min(4, valid - r0);
-        float* dst = A.out_u + (row0 + r0) * D;
-        for (int idx = lane; idx < nrow * D; idx += 32) {
-          const int rr = idx / D, j = idx - rr * D;
-          dst[idx] = gu[j * RP + r0 + rr];
-        }
-      }
-    }
-    if (BWD) {
-      __syncwarp();
-      nbar_arrive(CH_BAR_FULL + n_lin - 1, NB);
-    }
-    stamp(4);
-
-    // ---- reverse pass
-    if (BWD) {
-      for (int k = L - 1; k >= 0; --k) {
-        const float* wb = w_acquire(req);
-        stamp(190 + k);
-        const float* slot = sm + P.o_slot + k * P.slot_stride;
-        const float* gx_k = gx + (k & 1) * P.DP * RP + r0;
-#pragma unroll UL
-        for (int ii = 0; ii < n_lin; ++ii) {
-          const int i = n_lin - 1 - ii;
-          if (i == 0 && k == 0) break;                  // nothing consumes the gradient w.r.t. the flow's input
-          const LinDesc& ln = P.lin[i];
-          const int tgt = i > 0 ? i - 1 : n_lin - 1;    // buffer this product's epilogue writes
-          const bool first_write = i > 0 && ti == 0 && k == L - 1;
-          stamp(200 + 10 * k + i);
-          if (!first_write) nbar_sync(CH_BAR_EMPTY + tgt, NB);
-          stamp(300 + 10 * k + i);
-          if (has_rows) {
-            const float* G = sm + P.o_gl[i] + r0;
-            const float* Wt = wb + ln.wt_off;
-            if (i > 0) {
-              // through the activation: g_a = g_h * act'(a)
-              const float* dsrc = slot + (RELU ? P.h_off[i] : P.d_off[i]) + r0;
-              float* gout = sm + P.o_gl[i - 1] + r0;
-              chain_gemm_cols(G, RP, Wt, ln.KP, A.cx[i], lane, [&](int c, int re, const float (&v)[2]) {
-                float dv[2], gv[2];
-                ldv(dv, dsrc + c * RP + re);
-#pragma unroll
-                for (int q = 0; q < 2; ++q) gv[q] = RELU ? (dv[q] > 0.f ? v[q] : 0.f) : v[q] * dv[q];
-                stv(gout + c * RP + re, gv);
-              });
-            } else {
-              // gradient w.r.t. this layer's input x_k (MADE path + direct path); x_k is layer k-1's flipped
-              // output: continue straight into that layer's elementwise reverse step
-              const float* pslot = sm + P.o_slot + (k - 1) * P.slot_stride + r0;
-              float* gx_p = gx + ((k - 1) & 1) * P.DP * RP + r0;
-              chain_gemm_cols(G, RP, Wt, ln.KP, A.cx[i], lane, [&](int c, int re, const float (&v)[2]) {
-                if (c < D) {
-                  float dv[2], sv[2], vv[2], o0[2], o1[2], gn[2];
-                  ldv(dv, gx_k + c * RP + re);
-                  const int j = P.reverse ? D - 1 - c : c;
-                  ldv(sv, pslot + P.s_off + j * RP + re);
-                  ldv(vv, pslot + P.v_off + j * RP + re);
-#pragma unroll
-                  for (int q = 0; q < 2; ++q) {
-                    const float gv = v[q] + dv[q];
-                    const bool okr = r0 + re + q < valid;
-                    o0[q] = okr ? -gv * sv[q] : 0.f;
-                    o1[q] = okr ? 0.5f * gv * vv[q] - 0.5f * A.inv_b : 0.f;
-                    gn[q] = okr ? gv * sv[q] : 0.f;
-                  }
-                  stv(obuf + r0 + j * RP + re, o0);
-                  stv(obuf + r0 + (D + j) * RP + re, o1);
-                  stv(gx_p + j * RP + re, gn);
-                }
-              });
+          const float lp = acc - (float)D * kHalfLog2Pi + A.logdet_const;
+          const bool lead = f0 == 0 && vok;
+          if (lead && A.out_logp) A.out_logp[row0 + r] = lp;
+          if (!BWD && lead && A.out_logdet) A.out_logdet[row0 + r] = ldsum;
+          if (BWD) my_loss += warp_sum(lead ? -lp * A.inv_b : 0.f);
+          if (!BWD && A.out_u) {   // own rows are contiguous in HBM
+            const int nrow = min(8, valid - r0);
+            float* dst = A.out_u + (row0 + r0) * D;
+            for (int idx = lane; idx < nrow * D; idx += 32) {
+              const int rr = idx / D, j = idx - rr * D;
+              dst[idx] = gu[j * RP + r0 + rr];
             }
           }
-          __syncwarp();
-          nbar_arrive(CH_BAR_FULL + tgt, NB);
-          stamp(400 + 10 * k + i);
         }
+        __syncwarp();
+        stamp(4);
+        rev = true;
+        k = L - 1;
+        i = n_lin - 1;
+        continue;
+      }
+
+      // ---- per-product bookkeeping: weight image, gradient-buffer hand-offs
+      const bool first_of_layer = rev ? i == n_lin - 1 : i == 0;
+      if (first_of_layer) {
+        wbuf_cur = w_acquire(req);
+        stamp((rev ? 190 : 90) + k);
+      }
+      bool skip = false;
+      if (BWD && rev && i == 0) {
+        // every gradient of this layer step is in its buffer set: hand it to the gradient warps
+        nbar_arrive(CH_BAR_FULL + (sq & 1), NB);
+        stamp(200 + 10 * k);
+        if (k == 0) skip = true;                        // nothing consumes the gradient w.r.t. the flow's input
+        else if (sq + 1 >= 2) nbar_sync(CH_BAR_EMPTY + ((sq + 1) & 1), NB);   // next set: previous content consumed
+        stamp(300 + 10 * k);
+      }
+
+      if (has_rows && !skip) {
+        const LinDesc& ln = P.lin[i];
+        float* slot = sm + P.o_slot + (BWD ? k : 0) * P.slot_stride;
+        const float* xin_k = sm + P.o_xin + k * P.xin_stride + r0;
+        // kind 0: forward hidden linear, 1: forward last linear + affine transform, 2: reverse through a hidden
+        // linear, 3: reverse through the first linear + the previous layer's elementwise step
+        const int kind = rev ? (i > 0 ? 2 : 3) : (i < n_lin - 1 ? 0 : 1);
+        const float* in;
+        const float* W;
+        int ldw;
+        const float* p0 = nullptr;   // kind 0/1: bias; 2: activation (derivative) rows; 3: previous layer's s rows
+        const float* p1 = nullptr;   // kind 3: previous layer's v rows
+        float* q0 = nullptr;         // kind 0: h out; 1: s out; 2: gradient out; 3: next set's obuf
+        float* q1 = nullptr;         // kind 0: act' out; 1: v out; 3: direct-path gradient of the previous layer
+        float* q2 = nullptr;         // kind 1: next layer's input
+        if (!rev) {
+          in = i == 0 ? xin_k : slot + P.h_off[i] + r0;
+          W = wbuf_cur + ln.w_off;
+          ldw = ln.NP;
+          p0 = wbuf_cur + ln.b_off;
+          if (kind == 0) {
+            q0 = slot + P.h_off[i + 1] + r0;
+            q1 = slot + P.d_off[i + 1] + r0;
+          } else {
+            q0 = slot + P.s_off + r0;
+            q1 = slot + P.v_off + r0;
+            q2 = ((k + 1 < L) ? sm + P.o_xin + (k + 1) * P.xin_stride : gu) + r0;
+          }
+        } else {
+          const float* gset = sm + P.o_gb + (sq & 1) * P.gb_stride;
+          in = gset + P.g_off[i] + r0;
+          W = wbuf_cur + ln.wt_off;
+          ldw = ln.KP;
+          if (kind == 2) {
+            p0 = slot + (RELU ? P.h_off[i] : P.d_off[i]) + r0;
+            q0 = sm + P.o_gb + (sq & 1) * P.gb_stride + P.g_off[i - 1] + r0;
+          } else {
+            const float* pslot = sm + P.o_slot + (k - 1) * P.slot_stride + r0;
+            p0 = pslot + P.s_off;
+            p1 = pslot + P.v_off;
+            q0 = sm + P.o_gb + ((sq + 1) & 1) * P.gb_stride + r0;
+            q1 = gx + ((k - 1) & 1) * P.DP * RP + r0;
+          }
+        }
+        const float* gx_k = gx + (k & 1) * P.DP * RP + r0;
+        const int N = ln.N;
+        chain_gemm(in, RP, W, ldw, rev ? A.cx[i] : A.cf[i], lane, [&](int c, int rr, const auto& v) {
+          constexpr int NR = sizeof(v[0]) / sizeof(float);
+          if (!rows_ok(rr)) return;
+          if (kind == 0) {
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc)
+              if (c + cc < N) {      // row N of the next operand is its ones row (bias gradient): pad columns stay out
+                const float bj = p0[c + cc];
+                float hv[NR], dv[NR];
+#pragma unroll
+                for (int q = 0; q < NR; ++q) act_eval<RELU>(P.act, v[cc][q] + bj, hv[q], dv[q]);
+                stv(q0 + (c + cc) * RP + rr, hv);
+                if (!RELU && BWD) stv(q1 + (c + cc) * RP + rr, dv);
+              }
+          } else if (kind == 1) {
+            // the last linear's image interleaves (mu_j, logp_j): the lane holds both; the affine autoregressive
+            // transform (jaxili/model.py:739-742) runs right here
+            const int j = c >> 1;
+            if (j < D) {
+              float bb[2], xv[NR], sv[NR], vv[NR], lv[NR];
+              ldv(bb, p0 + c);
+              ldv(xv, xin_k + j * RP + rr);
+              ldv(lv, ld + r0 + j * RP + rr);
+#pragma unroll
+              for (int q = 0; q < NR; ++q) {
+                const float lp = v[1][q] + bb[1];
+                sv[q] = expf(0.5f * lp);
+                vv[q] = (xv[q] - (v[0][q] + bb[0])) * sv[q];
+                lv[q] += 0.5f * lp;
+              }
+              if (BWD) {
+                stv(q0 + j * RP + rr, sv);
+                stv(q1 + j * RP + rr, vv);
+              }
+              stv(ld + r0 + j * RP + rr, lv);
+              const int jj = P.reverse ? D - 1 - j : j;
+              stv(q2 + jj * RP + rr, vv);
+            }
+          } else if (kind == 2) {
+            // through the activation: g_a = g_h * act'(a)
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              float dv[NR], gv[NR];
+              ldv(dv, p0 + (c + cc) * RP + rr);
+#pragma unroll
+              for (int q = 0; q < NR; ++q) gv[q] = RELU ? (dv[q] > 0.f ? v[cc][q] : 0.f) : v[cc][q] * dv[q];
+              stv(q0 + (c + cc) * RP + rr, gv);
+            }
+          } else {
+            // gradient w.r.t. this layer's input x_k (MADE path + direct path); x_k is layer k-1's flipped
+            // output: continue straight into that layer's elementwise reverse step
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc)
+              if (c + cc < D) {
+                float dv[NR], sv[NR], vv[NR], o0[NR], o1[NR], gn[NR];
+                ldv(dv, gx_k + (c + cc) * RP + rr);
+                const int j = P.reverse ? D - 1 - (c + cc) : (c + cc);
+                ldv(sv, p0 + j * RP + rr);
+                ldv(vv, p1 + j * RP + rr);
+#pragma unroll
+                for (int q = 0; q < NR; ++q) {
+                  const float gv = v[cc][q] + dv[q];
+                  const bool okr = r0 + rr + q < valid;
+                  o0[q] = okr ? -gv * sv[q] : 0.f;
+                  o1[q] = okr ? 0.5f * gv * vv[q] - 0.5f * A.inv_b : 0.f;
+                  gn[q] = okr ? gv * sv[q] : 0.f;
+                }
+                stv(q0 + j * RP + rr, o0);
+                stv(q0 + (D + j) * RP + rr, o1);
+                stv(q1 + j * RP + rr, gn);
+              }
+          }
+        });
+      }
+      __syncwarp();
+      stamp((rev ? 400 : 100) + 10 * k + i);
+
+      // ---- advance
+      const bool last_of_layer = rev ? i == 0 : i == n_lin - 1;
+      if (last_of_layer) {
         w_release(req);
         ++req;
+      }
+      if (!rev) {
+        if (++i == n_lin) { i = 0; ++k; }
+      } else {
+        if (--i < 0) { i = n_lin - 1; --k; ++sq; }
       }
     }
   }

@@ -44,12 +44,11 @@ struct FlowArgs {
     int nb_shift, nbg, nKG;   // column blocks per half-warp = 1<<nb_shift (<= 8), groups, row groups
     int bB;                   // weight gradient: warp blocks = nKG * nbg
   } ph[MAFB_MAX_LIN];
-  // chain kernel (chain_kernel.cuh): lane map of the row-owning warps per product.  A lane holds `groups` 4x4
-  // tiles of the warp's 4 rows and one of 1 << ks_shift parts of the reduction
+  // chain kernel (chain_kernel.cuh): lane map of the row-owning warps per product.  A lane holds an 8x4 tile of
+  // the warp's 8 rows and one of 1 << ks_shift parts of the reduction: lane = part * (32 >> ks_shift) + column slot
   struct ChainPh {
-    int ks_shift;             // 2: lane = part * 8 + column slot, 3: lane = part * 4 + column slot
-    int groups;               // column blocks per lane (1 or 2; 2 only with ks_shift == 2)
-    int n_pass;               // passes over the column blocks ((32 >> ks_shift) * groups per pass)
+    int ks_shift;             // 1, 2 or 3
+    int n_pass;               // passes over the column blocks (32 >> ks_shift per pass)
     int nsteps;               // reduction steps per lane = padded reduction length >> ks_shift
     int nCB;                  // column blocks
   } cf[MAFB_MAX_LIN], cx[MAFB_MAX_LIN];   // forward product, input-gradient product

@@ -171,8 +171,6 @@ bool plan_layout(Plan& P, int R, bool stash_all, int n_wbuf, int limit) {
   P.slot_stride = rows * RP;
   P.o_slot = o;
   o += (stash_all ? P.L : 1) * P.slot_stride;
-  P.o_obuf = o;
-  o += r4(2 * P.D) * RP;
   P.o_gu = o;
   o += P.DP * RP;
   P.o_gx = o;
@@ -185,16 +183,22 @@ bool plan_layout(Plan& P, int R, bool stash_all, int n_wbuf, int limit) {
   o += 32;
   P.o_gy = o;
   o += (r4(P.K0) - P.DP + 4) * RP;        // conditioner rows of the padded MADE input (dy mode)
-  P.o_g[0] = o;
-  o += maxhp * RP;
-  P.o_g[1] = o;
-  o += maxhp * RP;
-  // chain kernel: one gradient buffer per linear (its gradient warps consume them asynchronously)
+  // gradient buffers: [obuf | hidden-gradient buffers], twice for the chain kernel (set 1 only when every layer's
+  // activations are stashed -- the chain kernel's reverse pass needs that anyway)
+  P.o_obuf = o;
+  P.o_gb = o;
+  const int out_rows = r4(2 * P.D);
+  P.o_g[0] = o + out_rows * RP;
+  P.o_g[1] = P.o_g[0] + maxhp * RP;
+  int grows = out_rows;
   for (int i = 0; i < P.n_lin; ++i) {
-    if (i == P.n_lin - 1) P.o_gl[i] = P.o_obuf;
-    else if (i < 2) P.o_gl[i] = P.o_g[i];
-    else { P.o_gl[i] = o; o += P.lin[i].NP * RP; }
+    if (i == P.n_lin - 1) P.g_off[i] = 0;
+    else { P.g_off[i] = grows * RP; grows += P.lin[i].NP; }
   }
+  grows = std::max(grows, out_rows + 2 * maxhp);
+  P.gb_stride = grows * RP;
+  o += (stash_all ? 2 : 1) * P.gb_stride;
+  o += 8 * RP;                            // slack: strided tile loads of the chain kernel may run past a buffer's pad rows
   P.smem_bytes = MAFB_SMEM_HDR + o * 4;
   return P.smem_bytes <= limit;
 }
@@ -356,13 +360,8 @@ static void launch_flow(const Plan& P, const FlowArgs& A, int grid, cudaStream_t
   const bool relu = P.act == MAFB200_ACT_RELU;
   if (use_chain(P, A, BWD)) {
     constexpr int nt = BWD ? CH_NT_BWD : CH_NT_FWD;
-    if (P.n_lin == 3) {
-      if (relu) maf_chain_kernel<BWD, true, 3><<<grid, nt, P.smem_bytes, st>>>(P, A);
-      else maf_chain_kernel<BWD, false, 3><<<grid, nt, P.smem_bytes, st>>>(P, A);
-    } else {
-      if (relu) maf_chain_kernel<BWD, true, 0><<<grid, nt, P.smem_bytes, st>>>(P, A);
-      else maf_chain_kernel<BWD, false, 0><<<grid, nt, P.smem_bytes, st>>>(P, A);
-    }
+    if (relu) maf_chain_kernel<BWD, true><<<grid, nt, P.smem_bytes, st>>>(P, A);
+    else maf_chain_kernel<BWD, false><<<grid, nt, P.smem_bytes, st>>>(P, A);
     return;
   }
 #define LAUNCH(NT_, R_, L_) maf_flow_kernel<BWD, R_, NT_, L_><<<grid, NT_, P.smem_bytes, st>>>(P, A)
@@ -817,10 +816,9 @@ int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shi
     SET_FLOW(true, true, 3) SET_FLOW(true, false, 3) SET_FLOW(false, true, 3) SET_FLOW(false, false, 3)
     SET_FLOW(true, true, 0) SET_FLOW(true, false, 0) SET_FLOW(false, true, 0) SET_FLOW(false, false, 0)
 #undef SET_FLOW
-#define SET_CHAIN(B_, R_, L_) \
-  CUH(cudaFuncSetAttribute(maf_chain_kernel<B_, R_, L_>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    SET_CHAIN(true, true, 3) SET_CHAIN(true, false, 3) SET_CHAIN(false, true, 3) SET_CHAIN(false, false, 3)
-    SET_CHAIN(true, true, 0) SET_CHAIN(true, false, 0) SET_CHAIN(false, true, 0) SET_CHAIN(false, false, 0)
+#define SET_CHAIN(B_, R_) \
+  CUH(cudaFuncSetAttribute(maf_chain_kernel<B_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    SET_CHAIN(true, true) SET_CHAIN(true, false) SET_CHAIN(false, true) SET_CHAIN(false, false)
 #undef SET_CHAIN
   }
   if (have_sampler) {
@@ -1119,28 +1117,24 @@ static void fill_phases(const Plan& P, FlowArgs& A, bool want_dy = false, bool s
     ph.bB = skip_wgrad ? 0 : ph.nKG * ph.nbg;
   }
   // chain kernel: per product, the lane map that minimises passes x (FMA cycles + reduce/epilogue overhead)
-  auto pick = [](int nCB, int QP, bool pairs, FlowArgs::ChainPh& c) {
-    static const int cand[3][2] = {{2, 2}, {2, 1}, {3, 1}};   // {ks_shift, groups}
-    int best = -1, best_cost = 1 << 30;
-    for (int t = 0; t < 3; ++t) {
-      const int sh = cand[t][0], g = cand[t][1];
-      if (sh == 3 && (pairs || QP % 8)) continue;           // 8 parts: whole steps only, single columns
-      const int per_pass = (32 >> sh) * g;
+  auto pick = [](int nCB, int QP, FlowArgs::ChainPh& c) {
+    int best = 1, best_cost = 1 << 30;
+    for (int sh = 1; sh <= 2; ++sh) {
+      if (QP % (1 << sh)) continue;                       // whole steps only
+      const int per_pass = 32 >> sh;
       const int passes = (nCB + per_pass - 1) / per_pass;
-      const int cost = passes * ((QP >> sh) * 16 * g + 40 + 14 * g + (sh == 3 ? 10 : 0));
-      if (cost < best_cost) { best_cost = cost; best = t; }
+      const int cost = passes * ((QP >> sh) * 32 + 40 + 30 * sh);
+      if (cost < best_cost) { best_cost = cost; best = sh; }
     }
-    c.ks_shift = cand[best][0];
-    c.groups = cand[best][1];
-    const int per_pass = (32 >> c.ks_shift) * c.groups;
-    c.n_pass = (nCB + per_pass - 1) / per_pass;
-    c.nsteps = QP >> c.ks_shift;
+    c.ks_shift = best;
+    c.n_pass = (nCB + (32 >> best) - 1) / (32 >> best);
+    c.nsteps = QP >> best;
     c.nCB = nCB;
   };
   for (int i = 0; i < P.n_lin; ++i) {
     const LinDesc& ln = P.lin[i];
-    pick(ln.NP / 4, ln.KP, i == P.n_lin - 1, A.cf[i]);              // last linear: (mu, logp) column pairs
-    pick((i == 0 ? P.DP : ln.KP) / 4, ln.NP, false, A.cx[i]);
+    pick(ln.NP / 4, ln.KP, A.cf[i]);
+    pick((i == 0 ? P.DP : ln.KP) / 4, ln.NP, A.cx[i]);
   }
 }
 

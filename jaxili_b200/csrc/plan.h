@@ -47,8 +47,11 @@ struct Plan {
   int o_red;                    // [32] per-warp loss contributions of the finalize step
   int o_gy;                     // [round4(C)][RP]: gradient w.r.t. the standardised conditioner (dy mode)
   int o_g[2];                   // ping-pong [max HP][RP] hidden-gradient buffers (barrier-phased kernel)
-  int o_gl[MAFB_MAX_LIN];       // gradient w.r.t. the output of linear i, one buffer per linear (chain kernel);
-                                // o_gl[n_lin-1] == o_obuf, o_gl[0..1] alias o_g[0..1]
+  // chain kernel: two gradient-buffer sets (alternating per layer step); set b starts at o_gb + b * gb_stride,
+  // the gradient w.r.t. the output of linear i sits at g_off[i] inside a set (g_off[n_lin-1] == 0).
+  // Set 0 is the region [o_obuf, o_g[0], o_g[1]] of the barrier-phased kernel.
+  int o_gb, gb_stride;
+  int g_off[MAFB_MAX_LIN];
   int smem_bytes;
 };
 
