@@ -179,6 +179,12 @@ int mafb200_dp_error(mafb200_handle h, int32_t* out);
    fused narrow kernel).  No effect on models that use the fused kernel. */
 int mafb200_set_wide_core(mafb200_handle h, int32_t core);
 
+/* Two fused kernels serve the narrow path (csrc/flow_kernel.cuh: barrier-phased, csrc/chain_kernel.cuh: row-owning
+   warp pairs + asynchronous weight-gradient warps); same results to rounding.  mode 0 (default): chain kernel for
+   the training pass, barrier-phased kernel for forward-only launches; 1: barrier-phased always; 2: chain kernel
+   wherever it applies.  Also settable per process with MAFB200_FLOW=auto|phased|chain. */
+int mafb200_set_flow_kernel(mafb200_handle h, int32_t mode);
+
 /* test hook: one GEMM of the wide path (see mafb200.cu); not part of the reference-facing surface */
 int mafb200_debug_gemm(int32_t variant, int32_t core, const float* A, const float* B, float* C,
                        int32_t M, int32_t N, int32_t K, const float* zeros_n, const float* zeros_mn,

@@ -31,6 +31,8 @@ def build(force=False, verbose=False):
         cmd.insert(1, "-Xptxas=-v")
     if os.environ.get("MAFB_TRACE"):
         cmd.insert(1, "-DMAFB_TRACE")
+    if os.environ.get("MAFB_CTA_TIMES"):
+        cmd.insert(1, "-DMAFB_CTA_TIMES")
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)

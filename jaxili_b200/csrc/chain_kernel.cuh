@@ -6,33 +6,35 @@
 // chain of 15 forward + 15 reverse dependent linears: a design that spreads every linear over the whole CTA pays
 // a CTA barrier, a pipeline fill and a drain per linear (47 % barrier stall in round 1).  Here
 //
-//   * CHAIN warps own rows.  Warp c holds rows 8c..8c+7 through every linear of every layer, forward and
-//     reverse: the only synchronisation on the dependent chain is __syncwarp.  One chain warp per SM
-//     sub-partition, issued with priority (highest warp ids).  A lane holds 8 rows x 4 columns and one of 2, 4 or
-//     8 parts of the reduction (32 accumulators, 3 loads per 16 packed FFMA2); operands are prefetched through a
-//     4-stage register ring; the parts are combined by a shuffle reduce-scatter.
+//   * CHAIN warps own rows.  A PAIR of warps (c, c+4: same SM sub-partition) holds rows 8p..8p+7 through every
+//     linear of every layer, forward and reverse; the two warps split the output columns of a product and meet
+//     at a 64-thread named barrier -- the only synchronisation on the dependent chain.  Two chain warps per
+//     sub-partition hide each other's latencies (tests/micro/lone_warp.cu: one warp alone runs the inner loop at
+//     51 cycles per 16 FFMA2, two reach the pipe's 37.5), issued with priority (highest warp ids).
+//     A lane holds 8 rows x 4 columns and one of 4 parts of the reduction (32 accumulators, 3 loads per 16 packed
+//     FFMA2, operands prefetched through a register ring); a two-stage shuffle reduce-scatter leaves every lane
+//     2 columns x 2 rows per row block for the epilogue.
 //   * GRADIENT warps compute the weight/bias gradients [A;1]^T G, the only product that crosses rows: once per
 //     layer, all linears of the layer as one flat list of 8x4 tiles (one tile per lane, reduction over all rows
 //     of the tile, no cross-lane step).  They consume the gradient buffers asynchronously (two buffer sets,
 //     named barriers full[b] / empty[b]) and fill the issue slots the chain leaves empty.
 //   * one PRODUCER warp streams the weight images and the input tiles with bulk copies (TMA 1-D) behind
 //     full/empty mbarriers.
-// Everything is sized to keep the instruction stream FFMA2-dominated: round 1's kernel and the first versions of
-// this one issued 3-4 bookkeeping instructions per FFMA2 (ncu: 23-27 % FFMA2) and were issue/latency bound.
 #pragma once
 #include "common.cuh"
 #include "flow_kernel.cuh"
 
 namespace mafb {
 
-constexpr int CH_CW = 4;                         // chain warps: 8 rows each, 32-row tiles
-constexpr int CH_GW = 7;                         // gradient warps
+constexpr int CH_CW = 8;                         // chain warps: 4 pairs, 8 rows per pair, 32-row tiles
+constexpr int CH_GW = 6;                         // gradient warps (one 8x4 tile per lane covers a [50,50] layer in one round)
 constexpr int CH_NT_BWD = 32 * (1 + CH_GW + CH_CW);
 constexpr int CH_NT_FWD = 32 * (1 + CH_CW);
 constexpr int CH_BAR_FULL = 1;                   // named barriers: full[b] = 1 + b, empty[b] = 3 + b
 constexpr int CH_BAR_EMPTY = 3;
 constexpr int CH_BAR_TILE = 5;                   // gradient warps are done with the tile's stash
 constexpr int CH_BAR_CHAIN = 6;                  // chain warps only (loss hand-off at the end)
+constexpr int CH_BAR_PAIR = 7;                   // + pair index: the two warps of a row pair
 
 __device__ __forceinline__ void nbar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -64,13 +66,12 @@ __device__ __forceinline__ void ch_fma_tile(float (&acc)[4][4], const float (&a)
 }
 
 // n reduction steps of the lane's 8x4 tile (two 4x4 tiles sharing the weight operand); pa / pw advance by da / dw
-// floats per step.  Operands run through a 4-stage register ring: the loads of step s+4 are issued behind the FMAs
-// of step s, i.e. 3 steps (96 FMA-pipe cycles) ahead of their use.
+// floats per step.  An odd step is peeled off the front; the rest runs through a 2-stage register ring: the loads
+// of step s+2 are issued behind the FMAs of step s, one step (16 FFMA2 of this warp plus the partner warp's
+// share of the pipe) ahead of their use.
 __device__ __forceinline__ void ch_mac(float (&acc)[2][4][4], const float* __restrict__ pa,
                                        const float* __restrict__ pw, int n, int da, int dw) {
-  const int rem = n & 3;
-#pragma unroll 1
-  for (int u = 0; u < rem; ++u) {
+  if (n & 1) {
     float a0[4], a1[4], w[4];
     ldv(a0, pa);
     ldv(a1, pa + 4);
@@ -80,21 +81,21 @@ __device__ __forceinline__ void ch_mac(float (&acc)[2][4][4], const float* __res
     pa += da;
     pw += dw;
   }
-  int m = n - rem;                 // multiple of 4
+  int m = n & ~1;
   if (m == 0) return;
-  float a0[4][4], a1[4][4], w[4][4];
+  float a0[2][4], a1[2][4], w[2][4];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
+  for (int u = 0; u < 2; ++u) {
     ldv(a0[u], pa + u * da);
     ldv(a1[u], pa + u * da + 4);
     ldv(w[u], pw + u * dw);
   }
 #pragma unroll 1
-  for (m -= 4; m > 0; m -= 4) {
-    pa += 4 * da;
-    pw += 4 * dw;
+  for (m -= 2; m > 0; m -= 2) {
+    pa += 2 * da;
+    pw += 2 * dw;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 2; ++u) {
       ch_fma_tile(acc[0], a0[u], w[u]);
       ch_fma_tile(acc[1], a1[u], w[u]);
       ldv(a0[u], pa + u * da);
@@ -103,14 +104,14 @@ __device__ __forceinline__ void ch_mac(float (&acc)[2][4][4], const float* __res
     }
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
+  for (int u = 0; u < 2; ++u) {
     ch_fma_tile(acc[0], a0[u], w[u]);
     ch_fma_tile(acc[1], a1[u], w[u]);
   }
 }
 
-// Reduce-scatter stages of a 4x4 tile (acc[col][row]) over the lanes that hold its reduction parts:
-// stage 1 (partner lane ^ 16) keeps column pair hi1, stage 2 (lane ^ 8) row pair hi0, stage 3 (lane ^ 4) one column.
+// Reduce-scatter stages of a 4x4 tile (acc[col][row]) over the 4 lanes that hold its reduction parts:
+// stage 1 (partner lane ^ 16) keeps column pair `hi`, stage 2 (lane ^ 8) row pair `hi`.
 __device__ __forceinline__ void ch_rs_cols(const float (&acc)[4][4], bool hi, float (&t)[2][4]) {
 #pragma unroll
   for (int c = 0; c < 2; ++c)
@@ -132,53 +133,36 @@ __device__ __forceinline__ void ch_rs_rows(const float (&t)[2][4], bool hi, floa
     }
 }
 
-// One product of the chain for the warp's 8 rows: out[c][r] = sum_q in[q][r] * W[q][c], all column blocks.
-// lane = kq * (32 >> ks_shift) + column slot; the lane's reduction part is q = kq, kq + KS, ... (KS = 2 or 4).
-//   KS = 2: the lane ends with columns (ce, ce+1) x 4 rows per row block:  epi(ce, rr, v) with v[2 cols][4 rows]
-//   KS = 4: columns (ce, ce+1) x 2 rows per row block:                     epi(ce, rr, v) with v[2][2]
-// rr = first row (relative to the warp's 8 rows).  KS is a run-time value on purpose: the kernel holds ONE copy
-// of this code for all products of the chain (instruction-cache footprint).
+// One warp's share of a product of the chain, for the pair's 8 rows: out[c][r] = sum_q in[q][r] * W[q][c] for the
+// column blocks first .. first + nblk - 1.  lane = kq * 8 + column slot; the lane's reduction part is
+// q = kq, kq + 4, ...  After the reduce-scatter the lane owns columns (ce, ce+1) x 2 rows per row block:
+// epi(ce, rr, v) with v[2 cols][2 rows], rr = first row relative to the pair's 8 rows.
 template <class Epi>
 __device__ __forceinline__ void chain_gemm(const float* __restrict__ in, int RP, const float* __restrict__ W, int ldw,
-                                           const FlowArgs::ChainPh& ph, int lane, Epi&& epi) {
-  const int ks_shift = ph.ks_shift, nCB = ph.nCB, nsteps = ph.nsteps, n_pass = ph.n_pass;
-  const int cpl = 32 >> ks_shift;
-  const int cbl = lane & (cpl - 1);
-  const int kq = lane >> (5 - ks_shift);
+                                           int first, int nblk, int nsteps, int lane, Epi&& epi) {
+  const int cbl = lane & 7;
+  const int kq = lane >> 3;
   const bool b1 = (lane & 16) != 0, b0 = (lane & 8) != 0;
-  const float* pin = in + kq * RP;
-  const float* pW = W + kq * ldw;
-  const int da = RP << ks_shift, dw = ldw << ks_shift;
 #pragma unroll 1
-  for (int pass = 0; pass < n_pass; ++pass) {
+  for (int base = 0; base < nblk; base += 8) {
     float acc[2][4][4];
-    const int cb = pass * cpl + cbl;
-    const bool ok = cb < nCB;
-    const int c0 = 4 * (ok ? cb : nCB - 1);
+    const int cb = base + cbl;
+    const bool ok = cb < nblk;
+    const int c0 = 4 * (first + (ok ? cb : nblk - 1));
 #pragma unroll
     for (int g = 0; g < 2; ++g)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[g][j][i] = 0.f;
-    ch_mac(acc, pin, pW + c0, nsteps, da, dw);
+    ch_mac(acc, in + kq * RP, W + kq * ldw + c0, nsteps, 4 * RP, 4 * ldw);
     const int ce = c0 + (b1 ? 2 : 0);
-    float t[2][2][4];
-    ch_rs_cols(acc[0], b1, t[0]);
-    ch_rs_cols(acc[1], b1, t[1]);
-    if (ks_shift == 1) {
-      if (ok) {
-        epi(ce, 0, t[0]);
-        epi(ce, 4, t[1]);
-      }
-    } else {
-      float r[2][2][2];
-      ch_rs_rows(t[0], b0, r[0]);
-      ch_rs_rows(t[1], b0, r[1]);
-      if (ok) {
-        epi(ce, b0 ? 2 : 0, r[0]);
-        epi(ce, b0 ? 6 : 4, r[1]);
-      }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      float t[2][4], r[2][2];
+      ch_rs_cols(acc[g], b1, t);
+      ch_rs_rows(t, b0, r);
+      if (ok) epi(ce, 4 * g + (b0 ? 2 : 0), r);
     }
   }
 }
@@ -201,12 +185,13 @@ __device__ __forceinline__ void dw_tile(const float* __restrict__ A, int a_strid
     for (int j = 0; j < 4; ++j) ldv(gv[j], G + j * g_stride + r);
 #pragma unroll
     for (int i = 0; i < 8; ++i) ldv(av[i], A + i * a_stride + r);
+    // row pair outermost: 32 independent FFMA2 between two updates of the same accumulator pair
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int t = 0; t < 4; t += 2)
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int t = 0; t < 4; t += 2) ffma2(out[i][j], acc_odd[i][j], av[i][t], av[i][t + 1], gv[j][t], gv[j][t + 1]);
+        for (int j = 0; j < 4; ++j) ffma2(out[i][j], acc_odd[i][j], av[i][t], av[i][t + 1], gv[j][t], gv[j][t + 1]);
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -214,10 +199,19 @@ __device__ __forceinline__ void dw_tile(const float* __restrict__ A, int a_strid
     for (int j = 0; j < 4; ++j) out[i][j] += acc_odd[i][j];
 }
 
-template <bool BWD, bool RELU>
+// NLIN > 0 fixes the number of masked linears per MADE at compile time (the loops over them unroll and the
+// per-linear descriptors become constant-bank operands); NLIN == 0 reads it from the plan.
+template <bool BWD, bool RELU, int NLIN>
 __global__ void __launch_bounds__(BWD ? CH_NT_BWD : CH_NT_FWD, 1)
 maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+#ifdef MAFB_CTA_TIMES
+  if (A.trace && threadIdx.x == 0) {   // debug: %globaltimer at entry of every CTA
+    unsigned long long tns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+    A.trace[2 * blockIdx.x] = (long long)tns;
+  }
+#endif
   uint64_t* wfull = reinterpret_cast<uint64_t*>(smem_raw);   // [2] weight image landed
   uint64_t* wempty = wfull + 2;                              // [2] all chain warps are done with it
   uint64_t* sfull = wfull + 4;                               // [2] input tile landed
@@ -230,7 +224,8 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
   constexpr int NB = 32 * (GW + CH_CW);                      // threads on the full / empty / tile barriers
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = P.D, C = P.C, L = P.L, RP = P.RP;
-  const int n_lin = P.n_lin;
+  constexpr int UL = NLIN > 0 ? NLIN : 1;                    // unroll factor of the loops over the linears
+  const int n_lin = NLIN > 0 ? NLIN : P.n_lin;
   const int Rt = A.Rt;
   const long long row_base = A.batch_index ? (long long)(A.batch_index[0] % A.n_batches) * A.B : 0;
   const int grid = gridDim.x;
@@ -354,7 +349,7 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
     // features k = kb + i * nKB (i < 8; k == K is the ones row = bias), n = nb + j * nNB (j < 4): the rows one
     // warp instruction reads are consecutive features, which the pitch maps to distinct banks
     int n_tiles_layer = 0;
-#pragma unroll 1
+#pragma unroll UL
     for (int i = 0; i < n_lin; ++i) n_tiles_layer += ((P.lin[i].K + 8) >> 3) * (P.lin[i].NP >> 2);
     int sq = 0;
     for (int ti = 0; ti < my_n; ++ti) {
@@ -370,7 +365,7 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
           if (!active) g = 0;
           // which linear, which tile
           int li = 0, nKB = 1, nNB = 1, local = 0, base = 0;
-#pragma unroll 1
+#pragma unroll UL
           for (int i = 0; i < n_lin; ++i) {
             const int kbs = (P.lin[i].K + 8) >> 3, nbs = P.lin[i].NP >> 2;
             if (g >= base && g < base + kbs * nbs) { li = i; nKB = kbs; nNB = nbs; local = g - base; }
@@ -379,7 +374,7 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
           g = local;
           const int kb = g / nNB, nb = g - kb * nNB;
           int K = 0, N = 0, pw_off = 0, goff = 0, aoff = 0;
-#pragma unroll 1
+#pragma unroll UL
           for (int i = 0; i < n_lin; ++i)
             if (i == li) {
               K = P.lin[i].K; N = P.lin[i].N; pw_off = P.lin[i].pw_off; goff = P.g_off[i];
@@ -413,21 +408,29 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
       if (ti + 1 < my_n) nbar_arrive(CH_BAR_TILE, NB);
     }
     stamp_end();
+#ifdef MAFB_CTA_TIMES
+    if (A.trace && warp == 1 && lane == 0) {
+      unsigned long long tns;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+      A.trace[2 * blockIdx.x + 1] = (long long)tns;
+    }
+#endif
     return;
   }
 
   // ======================================================================== chain warps
   const int cw = warp - GW - 1;
+  const int pr = cw & 3, hf = cw >> 2;                // row pair, column half
   const int nRB = Rt / 4;
-  const bool has_rows = 2 * cw < nRB;
-  const bool rb1 = 2 * cw + 1 < nRB;                  // the warp's second row block exists in the tile
-  const int r0 = 8 * (has_rows ? cw : 0);
+  const bool has_rows = 2 * pr < nRB;
+  const bool rb1 = 2 * pr + 1 < nRB;                  // the pair's second row block exists in the tile
+  const bool own_rb = 2 * pr + hf < nRB;              // this warp's row block for the row-wise steps
+  const int r0 = 8 * (has_rows ? pr : 0);
   float* const gu = sm + P.o_gu;
   float* const gx = sm + P.o_gx;
   float* const ld = sm + P.o_ld;
   float my_loss = 0.f;
   int req = 0, sq = 0;
-  const int total_steps = my_n * L;
 
   auto w_acquire = [&](int s) -> const float* {
     const int buf = two_wbuf ? (s & 1) : 0;
@@ -439,8 +442,21 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
     __syncwarp();
     if (lane == 0) mbar_arrive(&wempty[two_wbuf ? (s & 1) : 0]);
   };
-  // rows rr .. rr+NR-1 of the warp (relative) exist in the tile?  (a row block is all or nothing)
+  auto pair_sync = [&]() { nbar_sync(CH_BAR_PAIR + pr, 64); };
+  // rows rr, rr+1 of the pair (relative) exist in the tile?  (a row block is all or nothing)
   auto rows_ok = [&](int rr) { return rr < 4 || rb1; };
+  // this warp's column blocks of a product: wide products are split between the pair's warps, narrow ones
+  // (all blocks fit the 8 column slots of one warp) are done by the first warp alone
+  auto my_blocks = [&](const FlowArgs::ChainPh& ph, int& first, int& nblk) {
+    if (ph.split) {
+      const int na = (ph.nCB + 1) >> 1;
+      first = hf ? na : 0;
+      nblk = hf ? ph.nCB - na : na;
+    } else {
+      first = 0;
+      nblk = hf ? 0 : ph.nCB;
+    }
+  };
 
   for (int ti = 0; ti < my_n; ++ti) {
     const int t = blockIdx.x + ti * grid;
@@ -450,246 +466,230 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
     // the previous tile's activations are still being read by the gradient warps
     if (BWD && ti > 0) nbar_sync(CH_BAR_TILE, NB);
 
-    // ---- stage in: own rows, raw [row][feature] -> standardised feature-major
+    // ---- stage in: this warp's row block, raw [row][feature] -> standardised feature-major
     stamp(1);
     mbar_wait(&sfull[ti & 1], (uint32_t)((ti >> 1) & 1));
     stamp(2);
-    if (has_rows) {
+    if (own_rb) {
       const float* st = sm + P.o_stage + (ti & 1) * P.stage_stride;
       float* xin0 = sm + P.o_xin;
-      const int r = r0 + (lane & 7);
-      if (r < Rt) {
-        const bool ok = r < valid;
-        for (int j = lane >> 3; j < D + C; j += 4) {
-          if (j < D) {
-            // distrax.ScalarAffine.inverse: (x - shift) * (1/scale)
-            xin0[j * RP + r] = ok ? (st[r * D + j] - cst[j]) * cst[D + j] : 0.f;
-            ld[j * RP + r] = 0.f;
-          } else {
-            // Standardizer: (y - mean) / std
-            const int c = j - D;
-            const float v = ok ? __fdiv_rn(st[P.R * D + r * C + c] - cst[2 * D + c], cst[2 * D + C + c]) : 0.f;
-            for (int l = 0; l < L; ++l) sm[P.o_xin + l * P.xin_stride + j * RP + r] = v;
-          }
+      const int r = r0 + 4 * hf + (lane & 3);
+      const bool ok = r < valid;
+      for (int j = lane >> 2; j < D + C; j += 8) {
+        if (j < D) {
+          // distrax.ScalarAffine.inverse: (x - shift) * (1/scale)
+          xin0[j * RP + r] = ok ? (st[r * D + j] - cst[j]) * cst[D + j] : 0.f;
+          ld[j * RP + r] = 0.f;
+        } else {
+          // Standardizer: (y - mean) / std
+          const int c = j - D;
+          const float v = ok ? __fdiv_rn(st[P.R * D + r * C + c] - cst[2 * D + c], cst[2 * D + C + c]) : 0.f;
+          for (int l = 0; l < L; ++l) sm[P.o_xin + l * P.xin_stride + j * RP + r] = v;
         }
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sempty[ti & 1]);
+    pair_sync();
+
+    // ---- forward through the L MAF layers
     stamp(3);
-
-    // ---- the chain as ONE rolled loop over its products: forward (k up, i up), the per-row finalize step, reverse
-    //      (k down, i down).  One copy of the product code serves them all; the epilogue is selected per product.
-    const int n_fwd = L * n_lin;
-    const int n_items = BWD ? 2 * n_fwd + 1 : n_fwd + 1;
-    int k = 0, i = 0;                // current layer / linear
-    bool rev = false;
-    const float* wbuf_cur = nullptr;
-#pragma unroll 1
-    for (int it = 0; it < n_items; ++it) {
-      if (it == n_fwd) {
-        // ---- log-probability per row (jaxili/model.py:919-921 + 1094-1098); seed of the reverse pass.
-        //      4 lanes per row stride the features; the last layer's elementwise reverse step is done here.
-        float* gset = sm + P.o_gb + (sq & 1) * P.gb_stride;          // gradient-buffer set of the coming layer step
-        if (BWD && sq >= 2) nbar_sync(CH_BAR_EMPTY + (sq & 1), NB);  // its previous content has been consumed
-        if (has_rows) {
-          const int r = r0 + (lane >> 2);
-          const int f0 = lane & 3;
-          const bool rok = r < Rt, vok = r < valid;
-          const float* pslot = sm + P.o_slot + (BWD ? L - 1 : 0) * P.slot_stride;
-          float* gx_l = gx + ((L - 1) & 1) * P.DP * RP;
-          float acc = 0.f, ldsum = 0.f;
-          if (rok)
-            for (int j = f0; j < D; j += 4) {
-              const float u = gu[j * RP + r];
-              const float l = ld[j * RP + r];
-              ldsum += l;
-              acc += l - 0.5f * u * u;
-              if (BWD) {
-                const float gv = vok ? u * A.inv_b : 0.f;
-                const int jm = P.reverse ? D - 1 - j : j;    // output j of the flow is MADE feature jm of the last layer
-                const float s = pslot[P.s_off + jm * RP + r], v = pslot[P.v_off + jm * RP + r];
-                gset[jm * RP + r] = vok ? -gv * s : 0.f;
-                gset[(D + jm) * RP + r] = vok ? 0.5f * gv * v - 0.5f * A.inv_b : 0.f;
-                gx_l[jm * RP + r] = vok ? gv * s : 0.f;
-              }
-            }
-#pragma unroll
-          for (int o = 1; o < 4; o <<= 1) {
-            acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            ldsum += __shfl_xor_sync(0xffffffffu, ldsum, o);
-          }
-          const float lp = acc - (float)D * kHalfLog2Pi + A.logdet_const;
-          const bool lead = f0 == 0 && vok;
-          if (lead && A.out_logp) A.out_logp[row0 + r] = lp;
-          if (!BWD && lead && A.out_logdet) A.out_logdet[row0 + r] = ldsum;
-          if (BWD) my_loss += warp_sum(lead ? -lp * A.inv_b : 0.f);
-          if (!BWD && A.out_u) {   // own rows are contiguous in HBM
-            const int nrow = min(8, valid - r0);
-            float* dst = A.out_u + (row0 + r0) * D;
-            for (int idx = lane; idx < nrow * D; idx += 32) {
-              const int rr = idx / D, j = idx - rr * D;
-              dst[idx] = gu[j * RP + r0 + rr];
-            }
-          }
-        }
-        __syncwarp();
-        stamp(4);
-        rev = true;
-        k = L - 1;
-        i = n_lin - 1;
-        continue;
-      }
-
-      // ---- per-product bookkeeping: weight image, gradient-buffer hand-offs
-      const bool first_of_layer = rev ? i == n_lin - 1 : i == 0;
-      if (first_of_layer) {
-        wbuf_cur = w_acquire(req);
-        stamp((rev ? 190 : 90) + k);
-      }
-      bool skip = false;
-      if (BWD && rev && i == 0) {
-        // every gradient of this layer step is in its buffer set: hand it to the gradient warps
-        nbar_arrive(CH_BAR_FULL + (sq & 1), NB);
-        stamp(200 + 10 * k);
-        if (k == 0) skip = true;                        // nothing consumes the gradient w.r.t. the flow's input
-        else if (sq + 1 >= 2) nbar_sync(CH_BAR_EMPTY + ((sq + 1) & 1), NB);   // next set: previous content consumed
-        stamp(300 + 10 * k);
-      }
-
-      if (has_rows && !skip) {
+    for (int k = 0; k < L; ++k) {
+      const float* wf = w_acquire(req);
+      stamp(90 + k);
+      float* slot = sm + P.o_slot + (BWD ? k : 0) * P.slot_stride;
+      const float* xin_k = sm + P.o_xin + k * P.xin_stride + r0;
+      float* xnext = ((k + 1 < L) ? sm + P.o_xin + (k + 1) * P.xin_stride : gu) + r0;
+      const float* in = xin_k;
+#pragma unroll UL
+      for (int i = 0; i < n_lin; ++i) {
         const LinDesc& ln = P.lin[i];
-        float* slot = sm + P.o_slot + (BWD ? k : 0) * P.slot_stride;
-        const float* xin_k = sm + P.o_xin + k * P.xin_stride + r0;
-        // kind 0: forward hidden linear, 1: forward last linear + affine transform, 2: reverse through a hidden
-        // linear, 3: reverse through the first linear + the previous layer's elementwise step
-        const int kind = rev ? (i > 0 ? 2 : 3) : (i < n_lin - 1 ? 0 : 1);
-        const float* in;
-        const float* W;
-        int ldw;
-        const float* p0 = nullptr;   // kind 0/1: bias; 2: activation (derivative) rows; 3: previous layer's s rows
-        const float* p1 = nullptr;   // kind 3: previous layer's v rows
-        float* q0 = nullptr;         // kind 0: h out; 1: s out; 2: gradient out; 3: next set's obuf
-        float* q1 = nullptr;         // kind 0: act' out; 1: v out; 3: direct-path gradient of the previous layer
-        float* q2 = nullptr;         // kind 1: next layer's input
-        if (!rev) {
-          in = i == 0 ? xin_k : slot + P.h_off[i] + r0;
-          W = wbuf_cur + ln.w_off;
-          ldw = ln.NP;
-          p0 = wbuf_cur + ln.b_off;
-          if (kind == 0) {
-            q0 = slot + P.h_off[i + 1] + r0;
-            q1 = slot + P.d_off[i + 1] + r0;
-          } else {
-            q0 = slot + P.s_off + r0;
-            q1 = slot + P.v_off + r0;
-            q2 = ((k + 1 < L) ? sm + P.o_xin + (k + 1) * P.xin_stride : gu) + r0;
-          }
-        } else {
-          const float* gset = sm + P.o_gb + (sq & 1) * P.gb_stride;
-          in = gset + P.g_off[i] + r0;
-          W = wbuf_cur + ln.wt_off;
-          ldw = ln.KP;
-          if (kind == 2) {
-            p0 = slot + (RELU ? P.h_off[i] : P.d_off[i]) + r0;
-            q0 = sm + P.o_gb + (sq & 1) * P.gb_stride + P.g_off[i - 1] + r0;
-          } else {
-            const float* pslot = sm + P.o_slot + (k - 1) * P.slot_stride + r0;
-            p0 = pslot + P.s_off;
-            p1 = pslot + P.v_off;
-            q0 = sm + P.o_gb + ((sq + 1) & 1) * P.gb_stride + r0;
-            q1 = gx + ((k - 1) & 1) * P.DP * RP + r0;
-          }
-        }
-        const float* gx_k = gx + (k & 1) * P.DP * RP + r0;
-        const int N = ln.N;
-        chain_gemm(in, RP, W, ldw, rev ? A.cx[i] : A.cf[i], lane, [&](int c, int rr, const auto& v) {
-          constexpr int NR = sizeof(v[0]) / sizeof(float);
-          if (!rows_ok(rr)) return;
-          if (kind == 0) {
+        const float* W = wf + ln.w_off;
+        const float* bias = wf + ln.b_off;
+        int first, nblk;
+        my_blocks(A.cf[i], first, nblk);
+        if (i < n_lin - 1) {
+          float* hout = slot + P.h_off[i + 1] + r0;
+          float* dout = slot + P.d_off[i + 1] + r0;
+          const int N = ln.N;
+          if (has_rows && nblk > 0)
+            chain_gemm(in, RP, W, ln.NP, first, nblk, A.cf[i].nsteps, lane, [&](int c, int rr, const float (&v)[2][2]) {
+              if (!rows_ok(rr)) return;
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc)
-              if (c + cc < N) {      // row N of the next operand is its ones row (bias gradient): pad columns stay out
-                const float bj = p0[c + cc];
-                float hv[NR], dv[NR];
+              for (int cc = 0; cc < 2; ++cc)
+                if (c + cc < N) {      // row N of the next operand is its ones row (bias gradient): pad columns stay out
+                  const float bj = bias[c + cc];
+                  float hv[2], dv[2];
 #pragma unroll
-                for (int q = 0; q < NR; ++q) act_eval<RELU>(P.act, v[cc][q] + bj, hv[q], dv[q]);
-                stv(q0 + (c + cc) * RP + rr, hv);
-                if (!RELU && BWD) stv(q1 + (c + cc) * RP + rr, dv);
-              }
-          } else if (kind == 1) {
-            // the last linear's image interleaves (mu_j, logp_j): the lane holds both; the affine autoregressive
-            // transform (jaxili/model.py:739-742) runs right here
-            const int j = c >> 1;
-            if (j < D) {
-              float bb[2], xv[NR], sv[NR], vv[NR], lv[NR];
-              ldv(bb, p0 + c);
-              ldv(xv, xin_k + j * RP + rr);
-              ldv(lv, ld + r0 + j * RP + rr);
-#pragma unroll
-              for (int q = 0; q < NR; ++q) {
-                const float lp = v[1][q] + bb[1];
-                sv[q] = expf(0.5f * lp);
-                vv[q] = (xv[q] - (v[0][q] + bb[0])) * sv[q];
-                lv[q] += 0.5f * lp;
-              }
-              if (BWD) {
-                stv(q0 + j * RP + rr, sv);
-                stv(q1 + j * RP + rr, vv);
-              }
-              stv(ld + r0 + j * RP + rr, lv);
-              const int jj = P.reverse ? D - 1 - j : j;
-              stv(q2 + jj * RP + rr, vv);
-            }
-          } else if (kind == 2) {
-            // through the activation: g_a = g_h * act'(a)
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              float dv[NR], gv[NR];
-              ldv(dv, p0 + (c + cc) * RP + rr);
-#pragma unroll
-              for (int q = 0; q < NR; ++q) gv[q] = RELU ? (dv[q] > 0.f ? v[cc][q] : 0.f) : v[cc][q] * dv[q];
-              stv(q0 + (c + cc) * RP + rr, gv);
-            }
-          } else {
-            // gradient w.r.t. this layer's input x_k (MADE path + direct path); x_k is layer k-1's flipped
-            // output: continue straight into that layer's elementwise reverse step
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc)
-              if (c + cc < D) {
-                float dv[NR], sv[NR], vv[NR], o0[NR], o1[NR], gn[NR];
-                ldv(dv, gx_k + (c + cc) * RP + rr);
-                const int j = P.reverse ? D - 1 - (c + cc) : (c + cc);
-                ldv(sv, p0 + j * RP + rr);
-                ldv(vv, p1 + j * RP + rr);
-#pragma unroll
-                for (int q = 0; q < NR; ++q) {
-                  const float gv = v[cc][q] + dv[q];
-                  const bool okr = r0 + rr + q < valid;
-                  o0[q] = okr ? -gv * sv[q] : 0.f;
-                  o1[q] = okr ? 0.5f * gv * vv[q] - 0.5f * A.inv_b : 0.f;
-                  gn[q] = okr ? gv * sv[q] : 0.f;
+                  for (int q = 0; q < 2; ++q) act_eval<RELU>(P.act, v[cc][q] + bj, hv[q], dv[q]);
+                  stv(hout + (c + cc) * RP + rr, hv);
+                  if (!RELU && BWD) stv(dout + (c + cc) * RP + rr, dv);
                 }
-                stv(q0 + j * RP + rr, o0);
-                stv(q0 + (D + j) * RP + rr, o1);
-                stv(q1 + j * RP + rr, gn);
+            });
+          in = hout;
+        } else {
+          // the last linear's image interleaves (mu_j, logp_j): a lane ends with both; the affine
+          // autoregressive transform (jaxili/model.py:739-742) runs right here
+          float* sbuf = slot + P.s_off + r0;
+          float* vbuf = slot + P.v_off + r0;
+          if (has_rows && nblk > 0)
+            chain_gemm(in, RP, W, ln.NP, first, nblk, A.cf[i].nsteps, lane, [&](int ce, int rr, const float (&v)[2][2]) {
+              const int j = ce >> 1;
+              if (j < D && rows_ok(rr)) {
+                float bb[2], xv[2], sv[2], vv[2], lv[2];
+                ldv(bb, bias + ce);
+                ldv(xv, xin_k + j * RP + rr);
+                ldv(lv, ld + r0 + j * RP + rr);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  const float lp = v[1][q] + bb[1];
+                  sv[q] = expf(0.5f * lp);
+                  vv[q] = (xv[q] - (v[0][q] + bb[0])) * sv[q];
+                  lv[q] += 0.5f * lp;
+                }
+                if (BWD) {
+                  stv(sbuf + j * RP + rr, sv);
+                  stv(vbuf + j * RP + rr, vv);
+                }
+                stv(ld + r0 + j * RP + rr, lv);
+                const int jj = P.reverse ? D - 1 - j : j;
+                stv(xnext + jj * RP + rr, vv);
               }
-          }
-        });
+            });
+        }
+        pair_sync();
+        stamp(100 + 10 * k + i);
       }
-      __syncwarp();
-      stamp((rev ? 400 : 100) + 10 * k + i);
+      w_release(req);
+      ++req;
+    }
 
-      // ---- advance
-      const bool last_of_layer = rev ? i == 0 : i == n_lin - 1;
-      if (last_of_layer) {
+    // ---- log-probability per row (jaxili/model.py:919-921 + 1094-1098); seed of the reverse pass.
+    //      This warp's row block, 8 lanes per row stride the features; the last layer's elementwise reverse step
+    //      is done here.
+    float* gset = sm + P.o_gb + (sq & 1) * P.gb_stride;          // gradient-buffer set of the coming layer step
+    if (BWD && sq >= 2) nbar_sync(CH_BAR_EMPTY + (sq & 1), NB);  // its previous content has been consumed
+    if (own_rb) {
+      const int r = r0 + 4 * hf + (lane >> 3);
+      const int f0 = lane & 7;
+      const bool vok = r < valid;
+      const float* pslot = sm + P.o_slot + (BWD ? L - 1 : 0) * P.slot_stride;
+      float* gx_l = gx + ((L - 1) & 1) * P.DP * RP;
+      float acc = 0.f, ldsum = 0.f;
+      for (int j = f0; j < D; j += 8) {
+        const float u = gu[j * RP + r];
+        const float l = ld[j * RP + r];
+        ldsum += l;
+        acc += l - 0.5f * u * u;
+        if (BWD) {
+          const float gv = vok ? u * A.inv_b : 0.f;
+          const int jm = P.reverse ? D - 1 - j : j;      // output j of the flow is MADE feature jm of the last layer
+          const float s = pslot[P.s_off + jm * RP + r], v = pslot[P.v_off + jm * RP + r];
+          gset[jm * RP + r] = vok ? -gv * s : 0.f;
+          gset[(D + jm) * RP + r] = vok ? 0.5f * gv * v - 0.5f * A.inv_b : 0.f;
+          gx_l[jm * RP + r] = vok ? gv * s : 0.f;
+        }
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        ldsum += __shfl_xor_sync(0xffffffffu, ldsum, o);
+      }
+      const float lp = acc - (float)D * kHalfLog2Pi + A.logdet_const;
+      const bool lead = f0 == 0 && vok;
+      if (lead && A.out_logp) A.out_logp[row0 + r] = lp;
+      if (!BWD && lead && A.out_logdet) A.out_logdet[row0 + r] = ldsum;
+      if (BWD) my_loss += warp_sum(lead ? -lp * A.inv_b : 0.f);
+      if (!BWD && A.out_u) {   // own rows are contiguous in HBM
+        const int rw = r0 + 4 * hf;
+        const int nrow = min(4, valid - rw);
+        float* dst = A.out_u + (row0 + rw) * D;
+        for (int idx = lane; idx < nrow * D; idx += 32) {
+          const int rr = idx / D, j = idx - rr * D;
+          dst[idx] = gu[j * RP + rw + rr];
+        }
+      }
+    }
+    if (BWD) pair_sync();
+    stamp(4);
+
+    // ---- reverse pass
+    if (BWD) {
+      for (int k = L - 1; k >= 0; --k, ++sq) {
+        const float* wb = w_acquire(req);
+        stamp(190 + k);
+        const float* slot = sm + P.o_slot + k * P.slot_stride;
+        const float* gx_k = gx + (k & 1) * P.DP * RP + r0;
+        gset = sm + P.o_gb + (sq & 1) * P.gb_stride;
+        float* gnext = sm + P.o_gb + ((sq + 1) & 1) * P.gb_stride;   // set of the next layer step (its obuf is written here)
+#pragma unroll UL
+        for (int ii = 0; ii < n_lin; ++ii) {
+          const int i = n_lin - 1 - ii;
+          const LinDesc& ln = P.lin[i];
+          if (i == 0) {
+            // every gradient of this layer step is in its buffer set: hand it to the gradient warps
+            nbar_arrive(CH_BAR_FULL + (sq & 1), NB);
+            stamp(200 + 10 * k);
+            if (k == 0) break;                          // nothing consumes the gradient w.r.t. the flow's input
+            if (sq + 1 >= 2) nbar_sync(CH_BAR_EMPTY + ((sq + 1) & 1), NB);   // next set: previous content consumed
+            stamp(300 + 10 * k);
+          }
+          int first, nblk;
+          my_blocks(A.cx[i], first, nblk);
+          if (has_rows && nblk > 0) {
+            const float* G = gset + P.g_off[i] + r0;
+            const float* Wt = wb + ln.wt_off;
+            if (i > 0) {
+              // through the activation: g_a = g_h * act'(a)
+              const float* dsrc = slot + (RELU ? P.h_off[i] : P.d_off[i]) + r0;
+              float* gout = gset + P.g_off[i - 1] + r0;
+              chain_gemm(G, RP, Wt, ln.KP, first, nblk, A.cx[i].nsteps, lane, [&](int c, int rr, const float (&v)[2][2]) {
+                if (!rows_ok(rr)) return;
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                  float dv[2], gv[2];
+                  ldv(dv, dsrc + (c + cc) * RP + rr);
+#pragma unroll
+                  for (int q = 0; q < 2; ++q) gv[q] = RELU ? (dv[q] > 0.f ? v[cc][q] : 0.f) : v[cc][q] * dv[q];
+                  stv(gout + (c + cc) * RP + rr, gv);
+                }
+              });
+            } else {
+              // gradient w.r.t. this layer's input x_k (MADE path + direct path); x_k is layer k-1's flipped
+              // output: continue straight into that layer's elementwise reverse step
+              const float* pslot = sm + P.o_slot + (k - 1) * P.slot_stride + r0;
+              float* gx_p = gx + ((k - 1) & 1) * P.DP * RP + r0;
+              float* onext = gnext + r0;
+              chain_gemm(G, RP, Wt, ln.KP, first, nblk, A.cx[i].nsteps, lane, [&](int c, int rr, const float (&v)[2][2]) {
+                if (!rows_ok(rr)) return;
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc)
+                  if (c + cc < D) {
+                    float dv[2], sv[2], vv[2], o0[2], o1[2], gn[2];
+                    ldv(dv, gx_k + (c + cc) * RP + rr);
+                    const int j = P.reverse ? D - 1 - (c + cc) : (c + cc);
+                    ldv(sv, pslot + P.s_off + j * RP + rr);
+                    ldv(vv, pslot + P.v_off + j * RP + rr);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                      const float gv = v[cc][q] + dv[q];
+                      const bool okr = r0 + rr + q < valid;
+                      o0[q] = okr ? -gv * sv[q] : 0.f;
+                      o1[q] = okr ? 0.5f * gv * vv[q] - 0.5f * A.inv_b : 0.f;
+                      gn[q] = okr ? gv * sv[q] : 0.f;
+                    }
+                    stv(onext + j * RP + rr, o0);
+                    stv(onext + (D + j) * RP + rr, o1);
+                    stv(gx_p + j * RP + rr, gn);
+                  }
+              });
+            }
+          }
+          pair_sync();
+          stamp(400 + 10 * k + i);
+        }
         w_release(req);
         ++req;
-      }
-      if (!rev) {
-        if (++i == n_lin) { i = 0; ++k; }
-      } else {
-        if (--i < 0) { i = n_lin - 1; --k; ++sq; }
       }
     }
   }
@@ -705,6 +705,13 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
   }
   stamp(99);
   stamp_end();
+#ifdef MAFB_CTA_TIMES
+  if (A.trace && cw == 0 && lane == 0) {
+    unsigned long long tns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+    A.trace[400 + blockIdx.x] = (long long)tns;
+  }
+#endif
 }
 
 }  // namespace mafb

@@ -44,13 +44,11 @@ struct FlowArgs {
     int nb_shift, nbg, nKG;   // column blocks per half-warp = 1<<nb_shift (<= 8), groups, row groups
     int bB;                   // weight gradient: warp blocks = nKG * nbg
   } ph[MAFB_MAX_LIN];
-  // chain kernel (chain_kernel.cuh): lane map of the row-owning warps per product.  A lane holds an 8x4 tile of
-  // the warp's 8 rows and one of 1 << ks_shift parts of the reduction: lane = part * (32 >> ks_shift) + column slot
+  // chain kernel (chain_kernel.cuh): per product of the row-owning warp pairs
   struct ChainPh {
-    int ks_shift;             // 1, 2 or 3
-    int n_pass;               // passes over the column blocks (32 >> ks_shift per pass)
-    int nsteps;               // reduction steps per lane = padded reduction length >> ks_shift
-    int nCB;                  // column blocks
+    int nsteps;               // reduction steps per lane = padded reduction length / 4
+    int nCB;                  // column blocks of the product
+    int split;                // 1: the pair's warps split the column blocks; 0: narrow product, one warp does it
   } cf[MAFB_MAX_LIN], cx[MAFB_MAX_LIN];   // forward product, input-gradient product
   long long* trace;           // debug: clock64 stamps of CTA 0 at phase boundaries (nullable)
 };

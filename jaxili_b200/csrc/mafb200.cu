@@ -51,6 +51,7 @@ struct mafb200_handle_s {
   Plan plan{};                  // one CTA per SM
   Plan plan2{};                 // two CTAs per SM (plan2.P == 0 when it does not fit)
   int occ_mode = 0;             // 0 auto, 1 / 2 forced (env MAFB200_OCC)
+  int flow_kernel = 0;          // 0 auto (chain for training, phased otherwise), 1 phased always, 2 chain wherever it applies
   SamplePlan splan{};
   SamplePackArgs spack{};
   int dims[MAFB_MAX_LIN + 1]{};
@@ -342,26 +343,30 @@ static size_t dp_slot_floats(const Plan& P) { return (size_t)((P.P + 3) & ~3) + 
 static size_t dp_recv_off(const Plan& P) { return 2 * dp_slot_floats(P) + 8; }
 static size_t dp_total_floats(const Plan& P) { return dp_recv_off(P) + 2 * (2 * DP_MAX_WORLD * dp_slot_floats(P)); }
 
-// 0: chain kernel where it applies (default), 1: always the barrier-phased kernel (env MAFB200_FLOW=phased)
-static int flow_mode() {
-  static const int mode = [] { const char* e = getenv("MAFB200_FLOW"); return (e && strcmp(e, "phased") == 0) ? 1 : 0; }();
-  return mode;
-}
-// the chain kernel serves forward-only launches on every plan and the reverse pass when every layer's
-// activations are stashed; the conditioner-gradient mode stays on the barrier-phased kernel
-static bool use_chain(const Plan& P, const FlowArgs& A, bool bwd) {
-  if (flow_mode() == 1 || P.threads != kFlowThreads) return false;
-  if (bwd && (!P.stash_all || A.out_dy)) return false;
-  return P.n_lin <= 6;
+// Which fused flow kernel serves a launch (mode: 0 auto, 1 barrier-phased always, 2 chain wherever it applies;
+// mafb200_set_flow_kernel / env MAFB200_FLOW=auto|phased|chain).  The chain kernel needs every layer's
+// activations stashed for the reverse pass; the conditioner-gradient mode stays on the barrier-phased kernel.
+// auto: chain for the training pass, barrier-phased for forward-only launches -- measured on B200
+// (tests/ab_flow.py): log_prob is 10-15 % faster on the phased kernel (16 warps on the products, no
+// weight-gradient work to overlap), the training pass 7-9 % faster on the chain kernel.
+static bool use_chain(int mode, const Plan& P, const FlowArgs& A, bool bwd) {
+  if (mode == 1 || P.threads != kFlowThreads) return false;
+  if (!bwd) return mode == 2;
+  return P.stash_all && !A.out_dy;
 }
 
 template <bool BWD>
-static void launch_flow(const Plan& P, const FlowArgs& A, int grid, cudaStream_t st) {
+static void launch_flow(int mode, const Plan& P, const FlowArgs& A, int grid, cudaStream_t st) {
   const bool relu = P.act == MAFB200_ACT_RELU;
-  if (use_chain(P, A, BWD)) {
+  if (use_chain(mode, P, A, BWD)) {
     constexpr int nt = BWD ? CH_NT_BWD : CH_NT_FWD;
-    if (relu) maf_chain_kernel<BWD, true><<<grid, nt, P.smem_bytes, st>>>(P, A);
-    else maf_chain_kernel<BWD, false><<<grid, nt, P.smem_bytes, st>>>(P, A);
+    if (P.n_lin == 3) {
+      if (relu) maf_chain_kernel<BWD, true, 3><<<grid, nt, P.smem_bytes, st>>>(P, A);
+      else maf_chain_kernel<BWD, false, 3><<<grid, nt, P.smem_bytes, st>>>(P, A);
+    } else {
+      if (relu) maf_chain_kernel<BWD, true, 0><<<grid, nt, P.smem_bytes, st>>>(P, A);
+      else maf_chain_kernel<BWD, false, 0><<<grid, nt, P.smem_bytes, st>>>(P, A);
+    }
     return;
   }
 #define LAUNCH(NT_, R_, L_) maf_flow_kernel<BWD, R_, NT_, L_><<<grid, NT_, P.smem_bytes, st>>>(P, A)
@@ -721,6 +726,7 @@ int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shi
   }
   if (h->wide || !make_plan(d, h->dims, h->plan2, 2) || !h->plan2.stash_all || h->plan2.R < 16) h->plan2.P = 0;
   if (const char* e = getenv("MAFB200_OCC")) h->occ_mode = atoi(e);
+  if (const char* e = getenv("MAFB200_FLOW")) h->flow_kernel = strcmp(e, "phased") == 0 ? 1 : strcmp(e, "chain") == 0 ? 2 : 0;
   const bool have_sampler = !h->wide && make_sample_plan(d, h->dims, h->splan);
   if (!have_sampler) h->splan.img_floats = 0;
   const Plan& P = h->plan;
@@ -816,9 +822,10 @@ int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shi
     SET_FLOW(true, true, 3) SET_FLOW(true, false, 3) SET_FLOW(false, true, 3) SET_FLOW(false, false, 3)
     SET_FLOW(true, true, 0) SET_FLOW(true, false, 0) SET_FLOW(false, true, 0) SET_FLOW(false, false, 0)
 #undef SET_FLOW
-#define SET_CHAIN(B_, R_) \
-  CUH(cudaFuncSetAttribute(maf_chain_kernel<B_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    SET_CHAIN(true, true) SET_CHAIN(true, false) SET_CHAIN(false, true) SET_CHAIN(false, false)
+#define SET_CHAIN(B_, R_, L_) \
+  CUH(cudaFuncSetAttribute(maf_chain_kernel<B_, R_, L_>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    SET_CHAIN(true, true, 3) SET_CHAIN(true, false, 3) SET_CHAIN(false, true, 3) SET_CHAIN(false, false, 3)
+    SET_CHAIN(true, true, 0) SET_CHAIN(true, false, 0) SET_CHAIN(false, true, 0) SET_CHAIN(false, false, 0)
 #undef SET_CHAIN
   }
   if (have_sampler) {
@@ -1027,6 +1034,13 @@ int mafb200_set_wide_core(mafb200_handle h, int32_t core) {
   return 0;
 }
 
+int mafb200_set_flow_kernel(mafb200_handle h, int32_t mode) {
+  if (!h) return fail("null handle");
+  if (mode < 0 || mode > 2) return fail("mode must be 0 (auto), 1 (barrier-phased) or 2 (chain)");
+  h->flow_kernel = mode;
+  return 0;
+}
+
 int64_t mafb200_param_count(mafb200_handle h) { return h ? h->plan.P : -1; }
 
 int mafb200_get_mask(mafb200_handle h, uint8_t* mask_host) {
@@ -1116,25 +1130,15 @@ static void fill_phases(const Plan& P, FlowArgs& A, bool want_dy = false, bool s
     ph.nKG = (ph.nKB + kpw - 1) / kpw;
     ph.bB = skip_wgrad ? 0 : ph.nKG * ph.nbg;
   }
-  // chain kernel: per product, the lane map that minimises passes x (FMA cycles + reduce/epilogue overhead)
-  auto pick = [](int nCB, int QP, FlowArgs::ChainPh& c) {
-    int best = 1, best_cost = 1 << 30;
-    for (int sh = 1; sh <= 2; ++sh) {
-      if (QP % (1 << sh)) continue;                       // whole steps only
-      const int per_pass = 32 >> sh;
-      const int passes = (nCB + per_pass - 1) / per_pass;
-      const int cost = passes * ((QP >> sh) * 32 + 40 + 30 * sh);
-      if (cost < best_cost) { best_cost = cost; best = sh; }
-    }
-    c.ks_shift = best;
-    c.n_pass = (nCB + (32 >> best) - 1) / (32 >> best);
-    c.nsteps = QP >> best;
-    c.nCB = nCB;
-  };
+  // chain kernel: reduction steps (4 parts) and the column split between the two warps of a row pair
   for (int i = 0; i < P.n_lin; ++i) {
     const LinDesc& ln = P.lin[i];
-    pick(ln.NP / 4, ln.KP, A.cf[i]);
-    pick((i == 0 ? P.DP : ln.KP) / 4, ln.NP, A.cx[i]);
+    A.cf[i].nsteps = ln.KP / 4;
+    A.cf[i].nCB = ln.NP / 4;
+    A.cf[i].split = A.cf[i].nCB > 8;
+    A.cx[i].nsteps = ln.NP / 4;
+    A.cx[i].nCB = (i == 0 ? P.DP : ln.KP) / 4;
+    A.cx[i].split = A.cx[i].nCB > 8;
   }
 }
 
@@ -1166,7 +1170,7 @@ int mafb200_forward(mafb200_handle h, const float* params, const float* x, const
   fill_phases(*pp, A);
   const Plan& P = *pp;
   if (h->timing && flow_timing_begin(h, st)) return 1;
-  launch_flow<false>(P, A, grid, st);
+  launch_flow<false>(h->flow_kernel, P, A, grid, st);
   CU(cudaGetLastError());
   if (h->timing) CU(cudaEventRecord(h->ev1, st));
   return 0;
@@ -1218,7 +1222,7 @@ int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, con
   fill_phases(*pp, A);
   const Plan& P = *pp;
   if (h->timing && flow_timing_begin(h, st)) return 1;
-  launch_flow<true>(P, A, grid, st);
+  launch_flow<true>(h->flow_kernel, P, A, grid, st);
   CU(cudaGetLastError());
   if (h->timing) CU(cudaEventRecord(h->ev1, st));
   const size_t sf = dp_slot_floats(P);
@@ -1261,7 +1265,7 @@ int mafb200_log_prob_grad_y(mafb200_handle h, const float* params, const float* 
   const Plan* pp;
   if (launch_geometry(h, B, pp, A.Rt, A.n_tiles, grid)) return 1;
   fill_phases(*pp, A, /*want_dy=*/true, /*skip_wgrad=*/true);
-  launch_flow<true>(*pp, A, grid, st);
+  launch_flow<true>(h->flow_kernel, *pp, A, grid, st);
   CU(cudaGetLastError());
   return 0;
 }
@@ -1370,7 +1374,7 @@ int mafb200_train_step(mafb200_handle h, float* params, const float* x, const fl
   if (launch_geometry(h, B, pp, A.Rt, A.n_tiles, grid)) return 1;
   fill_phases(*pp, A);
   if (h->timing && flow_timing_begin(h, st)) return 1;
-  launch_flow<true>(*pp, A, grid, st);
+  launch_flow<true>(h->flow_kernel, *pp, A, grid, st);
   CU(cudaGetLastError());
   if (h->timing) CU(cudaEventRecord(h->ev1, st));
   OptArgs O{opt->lr, opt->warmup, opt->decay_steps, opt->init_factor, opt->end_factor, opt->b1, opt->b2,

@@ -111,6 +111,10 @@ class MafEngine:
         """Wide path GEMM core: "tf32" (tcgen05, default) or "ffma" (FP32, exact)."""
         _lib.check(self.lib.mafb200_set_wide_core(self._h, {"ffma": 0, "tf32": 1}[core]))
 
+    def set_flow_kernel(self, mode):
+        """Fused-kernel selection: "auto" (chain kernel for training, barrier-phased otherwise), "phased", "chain"."""
+        _lib.check(self.lib.mafb200_set_flow_kernel(self._h, {"auto": 0, "phased": 1, "chain": 2}[mode]))
+
     def flow_timing(self, enable=True):
         _lib.check(self.lib.mafb200_flow_timing(self._h, 1 if enable else 0))
 

@@ -15,11 +15,16 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-def _engine(spec, std, device="cuda:0"):
+def _engine(spec, std, device="cuda:0", flow="auto"):
     from jaxili_b200.engine import MafEngine
-    return MafEngine(spec.n_in, spec.n_cond, spec.n_layers, spec.layers, spec.activation,
-                     spec.use_reverse, spec.seed, std.shift, std.scale, std.mean, std.std,
-                     device=torch.device(device))
+    eng = MafEngine(spec.n_in, spec.n_cond, spec.n_layers, spec.layers, spec.activation,
+                    spec.use_reverse, spec.seed, std.shift, std.scale, std.mean, std.std,
+                    device=torch.device(device))
+    eng.set_flow_kernel(flow)   # both fused kernels (barrier-phased, chain) serve every test they apply to
+    return eng
+
+
+FLOWS = ["phased", "chain"]
 
 
 def _t(a):
@@ -28,9 +33,10 @@ def _t(a):
 
 @pytest.mark.parametrize("name,B", [("c1", 128), ("c2", 4096), ("c3", 1000), ("c2", 7), ("c2", 33),
                                     ("ref_test", 10), ("c3", 16384)])
-def test_log_prob_matches_oracle(name, B):
+@pytest.mark.parametrize("flow", FLOWS)
+def test_log_prob_matches_oracle(name, B, flow):
     spec, flat, std, x, y = make_case(CONFIGS[name], B, seed=1)
-    eng = _engine(spec, std)
+    eng = _engine(spec, std, flow=flow)
     assert (eng.mask() == spec.flat_mask().astype(np.uint8)).all()
     lp = eng.log_prob(_t(flat), _t(x), _t(y)).cpu().numpy()
     ref = onp.nde_log_prob(spec, flat.astype(np.float64), std, x.astype(np.float64), y.astype(np.float64))
@@ -39,9 +45,10 @@ def test_log_prob_matches_oracle(name, B):
 
 
 @pytest.mark.parametrize("act", ["silu", "tanh", "gelu", "elu", "sigmoid", "softplus", "leaky_relu"])
-def test_log_prob_and_grad_activations(act):
+@pytest.mark.parametrize("flow", FLOWS)
+def test_log_prob_and_grad_activations(act, flow):
     spec, flat, std, x, y = make_case(CONFIGS["ref_test"], 50, seed=2, activation=act, use_reverse=False)
-    eng = _engine(spec, std)
+    eng = _engine(spec, std, flow=flow)
     lp = eng.log_prob(_t(flat), _t(x), _t(y)).cpu().numpy()
     ref = onp.nde_log_prob(spec, flat.astype(np.float64), std, x.astype(np.float64), y.astype(np.float64))
     assert rel_err(lp, ref) < TOL
@@ -55,9 +62,10 @@ def test_log_prob_and_grad_activations(act):
 
 @pytest.mark.parametrize("name,B", [("c1", 128), ("c2", 4096), ("c3", 16384), ("c2", 130), ("c2", 5),
                                     ("ref_test", 64)])
-def test_loss_and_grad_match_oracle(name, B):
+@pytest.mark.parametrize("flow", FLOWS)
+def test_loss_and_grad_match_oracle(name, B, flow):
     spec, flat, std, x, y = make_case(CONFIGS[name], B, seed=3)
-    eng = _engine(spec, std)
+    eng = _engine(spec, std, flow=flow)
     loss = torch.zeros(1, device="cuda:0")
     grad = torch.full((spec.n_params,), 7.0, device="cuda:0")
     eng.loss_grad(_t(flat), _t(x), _t(y), loss, grad)
@@ -298,11 +306,12 @@ def test_train_step_equals_loss_grad_plus_clip_adam(name, B, kind):
     (dict(n_in=6, n_cond=2, n_layers=2, layers=[40, 24, 16]), 129, "tanh"),     # three hidden layers: 4 masked linears
     (dict(n_in=5, n_cond=0, n_layers=3, layers=[32, 32, 32, 32]), 64, "silu"),  # unconditional, 5 masked linears
 ])
-def test_other_depths_use_the_rolled_kernel(cfg, B, act):
+@pytest.mark.parametrize("flow", FLOWS)
+def test_other_depths_use_the_rolled_kernel(cfg, B, act, flow):
     """`layers` of any length >= 1: the kernel is specialised for 3 masked linears per MADE and runs a
     rolled loop over the linears otherwise; forward, gradients and the conditioner gradient against the oracle."""
     spec, flat, std, x, y = make_case(cfg, B, seed=31, activation=act)
-    eng = _engine(spec, std)
+    eng = _engine(spec, std, flow=flow)
     yt = _t(y) if cfg["n_cond"] else None
     lp = eng.log_prob(_t(flat), _t(x), yt)
     ref = onp.nde_log_prob(spec, flat.astype(np.float64), std, x.astype(np.float64), y.astype(np.float64))
