@@ -286,6 +286,11 @@ int mafb200_sample_philox(mafb200_handle h, const float* params, uint64_t seed,
 /* FP32 FFMA micro-benchmark used as the roofline denominator (bench.py): runs `iters`
    dependent-chain-free FFMA blocks on every SM, returns achieved TFLOP/s. */
 int mafb200_ffma_peak(int device, int32_t iters, float* out_tflops);
+/* the same with packed FFMA2 (packed = 1: fma.rn.f32x2, what the fused kernels issue) or plain FFMA (packed = 0) */
+int mafb200_fp32_peak(int device, int32_t iters, int32_t packed, float* out_tflops);
+/* TF32 tcgen05 tensor-pipe peak (M=128, N=256, K=8 MMAs issued back to back on resident shared-memory operands):
+   roofline denominator of the wide path; `iters` k-blocks of 4 MMAs per CTA, one CTA per SM. */
+int mafb200_tf32_peak(int device, int32_t iters, float* out_tflops);
 
 #ifdef __cplusplus
 }

@@ -105,6 +105,8 @@ SYMBOLS = {
                                         C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int32,
                                         C.c_void_p]),
     "mafb200_ffma_peak": (C.c_int, [C.c_int, C.c_int32, C.POINTER(C.c_float)]),
+    "mafb200_fp32_peak": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
+    "mafb200_tf32_peak": (C.c_int, [C.c_int, C.c_int32, C.POINTER(C.c_float)]),
 }
 
 _lib = None

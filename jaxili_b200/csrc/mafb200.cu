@@ -1490,7 +1490,9 @@ int mafb200_sample_philox(mafb200_handle h, const float* params, uint64_t seed, 
                        stream);
 }
 
-int mafb200_ffma_peak(int device, int32_t iters, float* out_tflops) {
+// FP32 FMA-pipe peak measured live: the 4x4 register-tile outer product of the flow kernels' inner loops with
+// all-register operands, as plain FFMA (packed = 0) or packed FFMA2 (packed = 1, what the kernels issue)
+int mafb200_fp32_peak(int device, int32_t iters, int32_t packed, float* out_tflops) {
   if (!out_tflops || iters <= 0) return fail("bad argument");
   CU(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -1501,11 +1503,15 @@ int mafb200_ffma_peak(int device, int32_t iters, float* out_tflops) {
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0));
   CU(cudaEventCreate(&e1));
-  ffma_peak_kernel<<<blocks, threads>>>(buf, iters / 4 + 1, 1e-3f);   // warm-up
+  auto launch = [&](int n) {
+    if (packed) ffma2_peak_kernel<<<blocks, threads>>>(buf, n, 1e-3f);
+    else ffma_peak_kernel<<<blocks, threads>>>(buf, n, 1e-3f);
+  };
+  launch(iters / 4 + 1);   // warm-up
   float best = 0.f;
   for (int rep = 0; rep < 5; ++rep) {
     CU(cudaEventRecord(e0));
-    ffma_peak_kernel<<<blocks, threads>>>(buf, iters, 1e-3f);
+    launch(iters);
     CU(cudaEventRecord(e1));
     CU(cudaEventSynchronize(e1));
     float ms = 0.f;
@@ -1513,6 +1519,45 @@ int mafb200_ffma_peak(int device, int32_t iters, float* out_tflops) {
     const double flops = (double)blocks * threads * (double)iters * 8 * 16 * 2;
     best = std::max(best, (float)(flops / (ms * 1e-3) / 1e12));
   }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *out_tflops = best;
+  return 0;
+}
+
+int mafb200_ffma_peak(int device, int32_t iters, float* out_tflops) {
+  return mafb200_fp32_peak(device, iters, 0, out_tflops);
+}
+
+// TF32 tcgen05 tensor-pipe peak measured live (tf32_peak_kernel): burst figure of a kernel timed alone
+int mafb200_tf32_peak(int device, int32_t iters, float* out_tflops) {
+  if (!out_tflops || iters <= 0) return fail("bad argument");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail("this library is built for sm_100a (B200) only");
+  const int blocks = prop.multiProcessorCount;
+  const int smem = (128 + 256) * 32 * 4 + 1024;
+  CU(cudaFuncSetAttribute(tf32_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  float* buf = nullptr;
+  CU(cudaMalloc(&buf, blocks * 4));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  tf32_peak_kernel<<<blocks, 128, smem>>>(iters / 8 + 1, buf);   // warm-up
+  float best = 0.f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(e0));
+    tf32_peak_kernel<<<blocks, 128, smem>>>(iters, buf);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = (double)blocks * (double)iters * 4 * 2.0 * 128 * 256 * 8;
+    best = std::max(best, (float)(flops / (ms * 1e-3) / 1e12));
+  }
+  CU(cudaGetLastError());
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(buf);

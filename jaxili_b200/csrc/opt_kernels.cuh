@@ -245,4 +245,30 @@ __global__ void ffma_peak_kernel(float* out, int iters, float seed) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// the same outer product with packed FFMA2 (fma.rn.f32x2, what the flow kernels issue): 8 per 4x4 step
+__global__ void ffma2_peak_kernel(float* out, int iters, float seed) {
+  float a[4], w[4], acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a[i] = seed * (float)(threadIdx.x + i + 1);
+    w[i] = seed * (float)(threadIdx.x * 3 + i + 1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j][i] = (float)(i + j);
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; i += 2) ffma2(acc[j][i], acc[j][i + 1], a[i], a[i + 1], w[j], w[j]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += acc[j][i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace mafb

@@ -288,4 +288,55 @@ wide_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// TF32 tensor-pipe peak probe (roofline denominator of the wide path): every CTA keeps one A tile (128 x 32) and one
+// B tile (256 x 32) in shared memory (K-major, SWIZZLE_128B: the layout the forward product uses) and one lane issues
+// tcgen05.mma.kind::tf32 (M=128, N=256, K=8) back to back into two alternating TMEM accumulators -- no operand
+// traffic, so the result is the issue-bound tensor rate at the clocks the part sustains.  2*128*256*8 FLOP per MMA.
+__global__ void __launch_bounds__(128) tf32_peak_kernel(int iters, float* out) {
+  extern __shared__ unsigned char pk_raw[];
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(pk_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  float* t = reinterpret_cast<float*>(tiles);
+  for (int i = threadIdx.x; i < (128 + 256) * 32; i += blockDim.x) t[i] = 1e-3f * (float)((i * 37 + blockIdx.x) % 101 - 50);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy tile writes -> tensor-core reads
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc_instr_desc(128, 256, false, false);
+      const uint32_t a_addr = smem_u32(tiles), b_addr = a_addr + 128 * 32 * 4;
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = tc_smem_desc(a_addr + k * 32, 16, 1024, 2);
+          const uint64_t bd = tc_smem_desc(b_addr + k * 32, 16, 1024, 2);
+          tc_mma_tf32(tmem_base + (it & 1) * 256, ad, bd, idesc, it > 1 ? 1u : 0u);
+        }
+      }
+      tc_commit(&done_bar);
+    }
+    __syncwarp();
+    mbar_wait(&done_bar, 0);
+    tc_fence_after();
+    float v[32];
+    tc_ld32(tmem_base, v);          // warp 0 reads its own lane quadrant (TMEM lanes 0..31)
+    if (lane == 0) out[blockIdx.x] = v[0];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+}
+
 }  // namespace mafb

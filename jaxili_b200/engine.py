@@ -334,9 +334,24 @@ class MafEngine:
         return out
 
 
-def ffma_peak_tflops(device=0, iters=4096):
-    """Measured FP32 FFMA throughput of the GPU (register-tiled GEMM operand pattern)."""
+def ffma_peak_tflops(device=0, iters=4096, packed=False):
+    """Measured FP32 FMA-pipe throughput of the GPU (register-tiled GEMM operand pattern): plain FFMA or, with
+    packed=True, the packed FFMA2 the fused kernels issue."""
     lib = _lib.load()
     out = C.c_float()
-    _lib.check(lib.mafb200_ffma_peak(int(device), int(iters), C.byref(out)))
+    _lib.check(lib.mafb200_fp32_peak(int(device), int(iters), 1 if packed else 0, C.byref(out)))
+    return float(out.value)
+
+
+def fp32_peak_tflops(device=0):
+    """Roofline denominator of the fused kernels: the better of the FFMA and FFMA2 probes, and both figures."""
+    a, b = ffma_peak_tflops(device), ffma_peak_tflops(device, packed=True)
+    return max(a, b), {"ffma": a, "ffma2": b}
+
+
+def tf32_peak_tflops(device=0, iters=20000):
+    """Measured TF32 tcgen05 tensor-pipe throughput (resident operands, back-to-back MMAs)."""
+    lib = _lib.load()
+    out = C.c_float()
+    _lib.check(lib.mafb200_tf32_peak(int(device), int(iters), C.byref(out)))
     return float(out.value)
