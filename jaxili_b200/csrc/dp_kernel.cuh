@@ -270,6 +270,11 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
     }
     asm volatile("bar.sync 1, %0;" ::"n"(RED_IDX));
   }
+  // A peer went missing (time-out above, in any block of this rank): every block sees the error word behind the
+  // grid barrier and the whole rank leaves params / m / v / step / the weight images untouched -- a stale word must
+  // never reach the optimiser state.  The loss is NaN and mafb200_dp_error reports it to the host.
+  const bool dp_fail = DP && __ldcg(a.error) != 0u;
+  if (dp_fail && blockIdx.x == 0 && i == 0) loss[0] = __int_as_float(0x7fc00000);
   // every block sums the norm partials in the same fixed order -> identical scale everywhere
   float ns = 0.f;
   for (int q = i; q < (int)gridDim.x; q += RED_IDX) ns += __ldcg(normpart + q);
@@ -283,7 +288,7 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
   }
   asm volatile("bar.sync 1, %0;" ::"n"(RED_IDX));
   const float gnorm = s_norm;
-  if (idx < P.P) {
+  if (idx < P.P && !dp_fail) {
     if (!(gnorm < O.clip)) g = (g / gnorm) * O.clip;
     const float lr_t = lr_schedule(O, t);
     float upd;
@@ -305,7 +310,7 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
     write_image(P, wimg, idx, mk ? pv : 0.f);
   }
   // every block read step[0] before the barrier
-  if (blockIdx.x == 0 && i == 0) step[0] = t + 1;
+  if (blockIdx.x == 0 && i == 0 && !dp_fail) step[0] = t + 1;
   tstamp(6);
 }
 

@@ -93,6 +93,10 @@ struct mafb200_handle_s {
   float* w_gx = nullptr;        // [cap][D]
   float* w_ld = nullptr;        // [cap]
   float* w_g[2] = {nullptr, nullptr};   // [cap][max H] hidden-gradient ping-pong
+  float* w_g0 = nullptr;        // [cap][K0] full input gradient of a layer's first linear (conditioner-gradient mode)
+  float* w_zero = nullptr;      // [cap][K0] zeros (addend of that product)
+  float* w_dy = nullptr;        // [cap][C]  conditioner gradient summed over the layers
+  long long wcap_dy = 0;
   // optional CUDA-event bracket around the flow kernel alone (roofline measurement in bench.py)
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -508,8 +512,11 @@ int wide_gemm(mafb200_handle h, const GemmArgs& g, bool relu, int splits, cudaSt
 }
 
 // one chunk of rows through the whole flow; bwd: also the reverse pass accumulating into grad / loss
+// dy != nullptr: conditioner-gradient mode (jaxili/posterior/mcmc_posterior.py:139-159): reverse pass without weight
+// gradients, the first linear's input gradient covers all K0 columns, its y-part is summed over the layers
 int wide_chunk(mafb200_handle h, const float* x, const float* y, long long rows, float inv_b, bool bwd,
-               float* out_logp, float* out_u, float* out_logdet, float* loss, float* grad, cudaStream_t st) {
+               float* out_logp, float* out_u, float* out_logdet, float* loss, float* grad, cudaStream_t st,
+               float* dy = nullptr) {
   const Plan& P = h->plan;
   const bool relu = P.act == MAFB200_ACT_RELU;
   const int D = P.D, K0 = P.K0, L = P.L, n_lin = P.n_lin;
@@ -563,7 +570,7 @@ int wide_chunk(mafb200_handle h, const float* x, const float* y, long long rows,
   }
   if (out_u) CU(cudaMemcpyAsync(out_u, h->w_u, (size_t)rows * D * 4, cudaMemcpyDeviceToDevice, st));
   if (out_logdet) CU(cudaMemcpyAsync(out_logdet, h->w_ld, (size_t)rows * 4, cudaMemcpyDeviceToDevice, st));
-  wide_final_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w, h->w_u, h->w_ld, out_logp, bwd ? loss : nullptr,
+  wide_final_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w, h->w_u, h->w_ld, out_logp, (bwd && !dy) ? loss : nullptr,
                                                                 bwd ? h->w_u : nullptr);
   CU(cudaGetLastError());
   if (!bwd) return 0;
@@ -584,7 +591,7 @@ int wide_chunk(mafb200_handle h, const float* x, const float* y, long long rows,
     for (int i = n_lin - 1; i >= 0; --i) {
       const LinDesc& ln = P.lin[i];
       const float* Ain = (i == 0) ? a0(k) : hbuf(h->w_h, k, i);
-      {  // weight gradient: dW = M * (A^T G), rows split over blockIdx.z
+      if (!dy) {  // weight gradient: dW = M * (A^T G), rows split over blockIdx.z
         GemmArgs g{};
         g.A = Ain; g.lda = ln.K;
         g.B = G; g.ldb = ln.N;
@@ -610,17 +617,116 @@ int wide_chunk(mafb200_handle h, const float* x, const float* y, long long rows,
           g.N = ln.K;
           g.C = h->w_g[i & 1]; g.ldc = ln.K;
           g.aux = relu ? hbuf(h->w_h, k, i) : hbuf(h->w_d, k, i); g.ldaux = ln.K;
-          g.colsum = gl + P.lin[i - 1].pb_off;      // db_{i-1} = column sums of g_a_{i-1}
+          g.colsum = dy ? nullptr : gl + P.lin[i - 1].pb_off;      // db_{i-1} = column sums of g_a_{i-1}
           if (wide_gemm<true, true, EPI_MUL_DERIV>(h, g, relu, 1, st)) return 1;
           G = g.C;
-        } else {
+        } else if (!dy) {
           g.N = D;                       // only the x part of the input carries gradient further
           g.C = h->w_u; g.ldc = D;
           g.aux = h->w_gx; g.ldaux = D;
           if (wide_gemm<true, true, EPI_ADD>(h, g, relu, 1, st)) return 1;
+        } else {
+          g.N = K0;                      // all columns: [d/dx | d/dy'] of this layer's MADE
+          g.C = h->w_g0; g.ldc = K0;
+          g.aux = h->w_zero; g.ldaux = K0;
+          if (wide_gemm<true, true, EPI_ADD>(h, g, relu, 1, st)) return 1;
+          const long long nx = rows * D, ny = rows * P.C;
+          wide_dx_pick_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(w, h->w_g0, h->w_gx, h->w_u);
+          wide_dy_accum_kernel<<<(unsigned)((ny + 255) / 256), 256, 0, st>>>(w, h->w_g0, h->w_dy, k == L - 1 ? 1 : 0);
+          CU(cudaGetLastError());
         }
       }
     }
+  }
+  if (dy) {
+    const long long ny = rows * P.C;
+    wide_dy_final_kernel<<<(unsigned)((ny + 255) / 256), 256, 0, st>>>(w, h->w_dy, h->stdc, dy);
+    CU(cudaGetLastError());
+  }
+  return 0;
+}
+
+int wide_ensure_dy_scratch(mafb200_handle h) {
+  if (h->wcap_dy >= h->wcap && h->w_g0) return 0;
+  const Plan& P = h->plan;
+  cudaFree(h->w_g0); cudaFree(h->w_zero); cudaFree(h->w_dy);
+  h->w_g0 = h->w_zero = h->w_dy = nullptr;
+  h->wcap_dy = 0;
+  const size_t c = (size_t)h->wcap;
+  CU(cudaMalloc(&h->w_g0, c * P.K0 * 4));
+  CU(cudaMalloc(&h->w_zero, c * P.K0 * 4));
+  CU(cudaMemset(h->w_zero, 0, c * P.K0 * 4));
+  CU(cudaMalloc(&h->w_dy, c * std::max(P.C, 1) * 4));
+  h->wcap_dy = h->wcap;
+  return 0;
+}
+
+int wide_log_prob_grad_y(mafb200_handle h, const float* params, const float* x, const float* y, int64_t B,
+                         float* out_logp, float* out_dy, int32_t flags, cudaStream_t st) {
+  if (!(flags & MAFB200_PACKED_CURRENT) && mafb200_pack(h, params, st)) return 1;
+  if (wide_ensure_scratch(h, B)) return 1;
+  if (wide_ensure_dy_scratch(h)) return 1;
+  const Plan& P = h->plan;
+  for (int64_t r0 = 0; r0 < B; r0 += h->wcap) {
+    const long long rows = std::min<long long>(h->wcap, B - r0);
+    // 1/B := -1: the "loss" is sum_b log p_b, whose y-gradient is per row (as on the fused path)
+    if (wide_chunk(h, x + r0 * P.D, y + r0 * P.C, rows, -1.f, true, out_logp ? out_logp + r0 : nullptr, nullptr,
+                   nullptr, nullptr, nullptr, st, out_dy + r0 * P.C))
+      return 1;
+  }
+  return 0;
+}
+
+// inverse flow of the wide path: per layer D sequential passes through the MADE's GEMM chain
+int wide_sample(mafb200_handle h, const float* params, const float* u, uint64_t seed, uint64_t row_offset,
+                const float* y_obs, int64_t n_obs, int64_t rows_per_obs, int64_t N, float* out, float* out_logdet,
+                int32_t flags, cudaStream_t st) {
+  if (!(flags & MAFB200_PACKED_CURRENT) && mafb200_pack(h, params, st)) return 1;
+  if (wide_ensure_scratch(h, N)) return 1;
+  const Plan& P = h->plan;
+  const bool relu = P.act == MAFB200_ACT_RELU;
+  const int D = P.D, K0 = P.K0, L = P.L, n_lin = P.n_lin;
+  const size_t cap = (size_t)h->wcap;
+  for (int64_t r0 = 0; r0 < N; r0 += h->wcap) {
+    const long long rows = std::min<long long>(h->wcap, N - r0);
+    WideCommon w{D, P.C, K0, P.reverse, rows, 1.f, h->logdet_const};
+    WideInvArgs a{u ? u + r0 * D : nullptr, seed, row_offset, y_obs, n_obs, rows_per_obs, r0};
+    const unsigned gr = (unsigned)((rows + 255) / 256), ge = (unsigned)((rows * D + 255) / 256);
+    wide_inv_prep_kernel<<<gr, 256, 0, st>>>(w, a, h->stdc, h->w_a0, h->w_u, h->w_ld);
+    CU(cudaGetLastError());
+    for (int k = L - 1; k >= 0; --k) {
+      const float* wl = h->wm + (size_t)k * P.ppl;
+      for (int d = 0; d < D; ++d) {
+        const float* in = h->w_a0;
+        int ld_in = K0;
+        size_t hoff = 0;
+        for (int i = 0; i < n_lin; ++i) {
+          const LinDesc& ln = P.lin[i];
+          GemmArgs g{};
+          g.A = in; g.lda = ld_in;
+          g.B = wl + ln.pw_off; g.ldb = ln.N;
+          g.M = (int)rows; g.N = ln.N; g.K = ln.K;
+          g.bias = wl + ln.pb_off;
+          g.act = P.act;
+          if (i < n_lin - 1) {
+            g.C = h->w_h + hoff; g.ldc = ln.N;
+            hoff += cap * ln.N;
+            if (wide_gemm<true, false, EPI_BIAS_ACT>(h, g, relu, 1, st)) return 1;
+            in = g.C; ld_in = ln.N;
+          } else {
+            g.C = h->w_o; g.ldc = ln.N;
+            if (wide_gemm<true, false, EPI_BIAS>(h, g, relu, 1, st)) return 1;
+          }
+        }
+        wide_inv_update_kernel<<<gr, 256, 0, st>>>(w, d, h->w_o, h->w_u, h->w_a0, h->w_ld);
+        CU(cudaGetLastError());
+      }
+      wide_inv_next_kernel<<<ge, 256, 0, st>>>(w, h->w_a0, h->w_u);
+      CU(cudaGetLastError());
+    }
+    wide_inv_final_kernel<<<ge, 256, 0, st>>>(w, h->w_u, h->w_ld, h->stdc, out + r0 * D,
+                                               out_logdet ? out_logdet + r0 : nullptr);
+    CU(cudaGetLastError());
   }
   return 0;
 }
@@ -863,6 +969,7 @@ int mafb200_destroy(mafb200_handle h) {
   cudaFree(h->w_a0); cudaFree(h->w_h); cudaFree(h->w_d); cudaFree(h->w_s); cudaFree(h->w_v);
   cudaFree(h->w_o); cudaFree(h->w_u); cudaFree(h->w_gx); cudaFree(h->w_ld);
   cudaFree(h->w_g[0]); cudaFree(h->w_g[1]);
+  cudaFree(h->w_g0); cudaFree(h->w_zero); cudaFree(h->w_dy);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
@@ -1243,9 +1350,9 @@ int mafb200_log_prob_grad_y(mafb200_handle h, const float* params, const float* 
                             float* out_logp, float* out_dy, int32_t flags, void* stream) {
   if (!h || !params || !x || !y || !out_dy) return fail("null argument");
   if (h->desc.n_cond == 0) return fail("the model has no conditioning input");
-  if (h->wide) return fail("log_prob_grad_y is implemented on the fused (narrow) path only");
   if (B <= 0) return B == 0 ? 0 : fail("negative batch");
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->wide) return wide_log_prob_grad_y(h, params, x, y, B, out_logp, out_dy, flags, st);
   if (!(flags & MAFB200_PACKED_CURRENT) && mafb200_pack(h, params, stream)) return 1;
   FlowArgs A{};
   A.wimg = h->wimg;
@@ -1437,11 +1544,13 @@ static int sample_common(mafb200_handle h, const float* params, const float* u, 
                          uint64_t row_offset, const float* y_obs, int64_t n_obs, int64_t rows_per_obs,
                          int64_t N, float* out, float* out_logdet, int32_t flags, void* stream) {
   if (!h || !params || !out || (h->desc.n_cond && !y_obs)) return fail("null argument");
-  if (h->splan.img_floats == 0) return fail("sampler not available for this configuration");
   if (N <= 0) return N == 0 ? 0 : fail("negative sample count");
   if (n_obs <= 0 || rows_per_obs <= 0 || n_obs * rows_per_obs < N)
     return fail("need n_obs * rows_per_obs >= N");
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->wide)   // models that do not fit shared memory: D sequential passes through the GEMM chain per layer
+    return wide_sample(h, params, u, seed, row_offset, y_obs, n_obs, rows_per_obs, N, out, out_logdet, flags, st);
+  if (h->splan.img_floats == 0) return fail("sampler not available for this configuration");
   const Plan& P = h->plan;
   const SamplePlan& S = h->splan;
   if (!(flags & MAFB200_PACKED_CURRENT)) {

@@ -11,6 +11,7 @@
 // This file is the FP32-FFMA core (exact parity with the oracle); the tcgen05 TF32 core replaces the
 // mainloop for the large shapes (wide_tc.cuh).
 #pragma once
+#include <curand_kernel.h>
 #include "common.cuh"
 
 namespace mafb {
@@ -321,6 +322,114 @@ __global__ void wide_pack_kernel(const float* __restrict__ params, const unsigne
                                  float* __restrict__ wm, int P) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < P) wm[idx] = mask[idx] ? params[idx] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Inverse flow of the wide path (jaxili/model.py:745-773, 876-901, 923-947, 1116-1126): per MAF layer D
+// sequential passes through the layer-by-layer MADE; pass d fixes x[:, d] = mu_d + exp(min(-logp_d / 2, 10)) u_d.
+
+struct WideInvArgs {
+  const float* u;                   // [N][D] base noise or nullptr -> Philox4x32-10, subsequence = global row
+  unsigned long long seed, row_offset;
+  const float* y_obs;               // [n_obs][C]
+  long long n_obs, rows_per_obs;
+  long long row0;                   // global index of this chunk's first row
+};
+
+// z <- base noise, a0 <- [0 | y'], log-det accumulator <- 0
+__global__ void wide_inv_prep_kernel(WideCommon w, WideInvArgs a, const float* __restrict__ stdc,
+                                     float* __restrict__ a0, float* __restrict__ z, float* __restrict__ ld) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= w.B) return;
+  const int D = w.D, C = w.C;
+  float* zr = z + r * D;
+  if (a.u) {
+    const float* src = a.u + r * D;
+    for (int j = 0; j < D; ++j) zr[j] = src[j];
+  } else {
+    curandStatePhilox4_32_10_t st;
+    curand_init(a.seed, a.row_offset + (unsigned long long)(a.row0 + r), 0ULL, &st);
+    for (int j = 0; j < D; j += 4) {
+      const float4 n4 = curand_normal4(&st);
+      zr[j] = n4.x;
+      if (j + 1 < D) zr[j + 1] = n4.y;
+      if (j + 2 < D) zr[j + 2] = n4.z;
+      if (j + 3 < D) zr[j + 3] = n4.w;
+    }
+  }
+  long long obs = (a.row0 + r) / a.rows_per_obs;
+  if (obs >= a.n_obs) obs = a.n_obs - 1;
+  float* ar = a0 + r * w.K0;
+  for (int j = 0; j < D; ++j) ar[j] = 0.f;
+  for (int c = 0; c < C; ++c) ar[D + c] = __fdiv_rn(a.y_obs[obs * C + c] - stdc[2 * D + c], stdc[2 * D + C + c]);
+  ld[r] = 0.f;
+}
+
+// pass d of one layer: x_d = mu_d + exp(m_d) * u_d, m = min(-logp / 2, 10); the last pass adds sum_j m_j to the
+// log-determinant (every logp_j of that pass is final: it depends on x_<j only)
+__global__ void wide_inv_update_kernel(WideCommon w, int d, const float* __restrict__ o, const float* __restrict__ z,
+                                       float* __restrict__ a0, float* __restrict__ ld) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= w.B) return;
+  const int D = w.D;
+  const float* orow = o + r * 2 * D;
+  const float m = fminf(-0.5f * orow[D + d], 10.f);
+  const float zs = z[r * D + (w.reverse ? D - 1 - d : d)];      // u <- u[:, ::-1] before the passes (model.py:765)
+  a0[r * w.K0 + d] = orow[d] + expf(m) * zs;
+  if (d == D - 1) {
+    float acc = 0.f;
+    for (int j = 0; j < D; ++j) acc += fminf(-0.5f * orow[D + j], 10.f);
+    ld[r] += acc;
+  }
+}
+
+// layer done: its x becomes the next layer's u; the MADE input starts from zero again
+__global__ void wide_inv_next_kernel(WideCommon w, float* __restrict__ a0, float* __restrict__ z) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= w.B * w.D) return;
+  const long long r = idx / w.D;
+  const int j = (int)(idx - r * w.D);
+  z[idx] = a0[r * w.K0 + j];
+  a0[r * w.K0 + j] = 0.f;
+}
+
+// theta = scale * x + shift (distrax.ScalarAffine.forward, model.py:1122-1126)
+__global__ void wide_inv_final_kernel(WideCommon w, const float* __restrict__ z, const float* __restrict__ ld,
+                                      const float* __restrict__ stdc, float* __restrict__ out,
+                                      float* __restrict__ out_logdet) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= w.B * w.D) return;
+  const long long r = idx / w.D;
+  const int j = (int)(idx - r * w.D);
+  out[idx] = stdc[2 * w.D + 2 * w.C + j] * z[idx] + stdc[j];
+  if (out_logdet && j == 0) out_logdet[r] = ld[r];
+}
+
+// conditioner gradient of the wide path: sum over the layers of the y-columns of the first linear's input
+// gradient, d/dy = (d/dy') / std
+__global__ void wide_dy_accum_kernel(WideCommon w, const float* __restrict__ g0, float* __restrict__ acc, int first) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= w.B * w.C) return;
+  const long long r = idx / w.C;
+  const int c = (int)(idx - r * w.C);
+  const float v = g0[r * w.K0 + w.D + c];
+  acc[idx] = first ? v : acc[idx] + v;
+}
+__global__ void wide_dy_final_kernel(WideCommon w, const float* __restrict__ acc, const float* __restrict__ stdc,
+                                     float* __restrict__ out_dy) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= w.B * w.C) return;
+  const int c = (int)(idx % w.C);
+  out_dy[idx] = __fdiv_rn(acc[idx], stdc[2 * w.D + w.C + c]);
+}
+// x-part of a [rows][K0] input gradient -> [rows][D] (+ the direct-path gradient)
+__global__ void wide_dx_pick_kernel(WideCommon w, const float* __restrict__ g0, const float* __restrict__ gxdir,
+                                    float* __restrict__ gu) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= w.B * w.D) return;
+  const long long r = idx / w.D;
+  const int j = (int)(idx - r * w.D);
+  gu[idx] = g0[r * w.K0 + j] + gxdir[idx];
 }
 
 }  // namespace mafb

@@ -129,8 +129,8 @@ class MafEngine:
         _lib.check(self.lib.mafb200_pack(self._h, self._chk(params, "params"), self._stream()))
 
     def log_prob(self, params, x, y, out=None, packed_current=False):
-        px = self._chk(x, "x", self.n_in)
-        py = self._chk(y, "y", self.n_cond) if self.n_cond else None
+        px = self._chk(x, "x", self.n_in, align=4)     # misaligned row tiles take the kernels' element-wise staging path
+        py = self._chk(y, "y", self.n_cond, align=4) if self.n_cond else None
         B = x.shape[0]
         if self.n_cond and y.shape[0] != B:
             raise ValueError("x and y must have the same number of rows")
@@ -144,8 +144,8 @@ class MafEngine:
 
     def forward(self, params, x, y, packed_current=False):
         """ConditionalMAF.__call__: returns (u, log_det) for standardised-or-not inputs."""
-        px = self._chk(x, "x", self.n_in)
-        py = self._chk(y, "y", self.n_cond) if self.n_cond else None
+        px = self._chk(x, "x", self.n_in, align=4)     # misaligned row tiles take the kernels' element-wise staging path
+        py = self._chk(y, "y", self.n_cond, align=4) if self.n_cond else None
         B = x.shape[0]
         u = torch.empty((B, self.n_in), dtype=torch.float32, device=self.device)
         ld = torch.empty(B, dtype=torch.float32, device=self.device)
@@ -158,7 +158,7 @@ class MafEngine:
     def inverse(self, params, u, y, packed_current=False):
         """ConditionalMAF.backward with per-row conditioning: returns (x, log_det)."""
         pu = self._chk(u, "u", self.n_in)
-        py = self._chk(y, "y", self.n_cond) if self.n_cond else None
+        py = self._chk(y, "y", self.n_cond, align=4) if self.n_cond else None
         N = u.shape[0]
         if self.n_cond and y.shape[0] != N:
             raise ValueError("u and y must have the same number of rows")
@@ -172,8 +172,8 @@ class MafEngine:
 
     def log_prob_grad_y(self, params, x, y, packed_current=False):
         """(log_prob [B], d log_prob / d y [B, n_cond]): gradient w.r.t. the conditioning input."""
-        px = self._chk(x, "x", self.n_in)
-        py = self._chk(y, "y", self.n_cond)
+        px = self._chk(x, "x", self.n_in, align=4)     # misaligned row tiles take the kernels' element-wise staging path
+        py = self._chk(y, "y", self.n_cond, align=4)
         B = x.shape[0]
         if y.shape[0] != B:
             raise ValueError("x and y must have the same number of rows")
@@ -190,7 +190,7 @@ class MafEngine:
         ``state``: dict of CUDA tensors eps[1], inv_mass[C], prior_kind[C] (int32), lo[C], hi[C], z[n,C],
         p[n,C], g[n,C], logdens[n], theta[n,C], scratch[n*(C+1)] -- updated in place."""
         n = state["z"].shape[0]
-        px = self._chk(x_rep, "x", self.n_in)
+        px = self._chk(x_rep, "x", self.n_in, align=4)
         if x_rep.shape[0] != n:
             raise ValueError("x must hold one observation row per chain")
         st = _lib.MafHmcState()
@@ -243,8 +243,8 @@ class MafEngine:
                   batch_index=None, n_batches=1, packed_current=False, dp_slot=False):
         """out_loss[0], out_grad <- NLL and its gradient over rows [0, batch_rows) of x/y (or the
         device-selected batch ``batch_index[0] % n_batches``)."""
-        px = self._chk(x, "x", self.n_in)
-        py = self._chk(y, "y", self.n_cond) if self.n_cond else None
+        px = self._chk(x, "x", self.n_in, align=4)     # misaligned row tiles take the kernels' element-wise staging path
+        py = self._chk(y, "y", self.n_cond, align=4) if self.n_cond else None
         B = x.shape[0] if batch_rows is None else int(batch_rows)
         if batch_index is not None:
             if x.shape[0] < B * n_batches:
@@ -275,8 +275,8 @@ class MafEngine:
         done, ``inv_global_b`` = 1 / global batch); the exchange happens inside the tail kernel."""
         if step.dtype != torch.int32 or not step.is_cuda:
             raise TypeError("step must be an int32 CUDA tensor")
-        px = self._chk(x, "x", self.n_in)
-        py = self._chk(y, "y", self.n_cond) if self.n_cond else None
+        px = self._chk(x, "x", self.n_in, align=4)     # misaligned row tiles take the kernels' element-wise staging path
+        py = self._chk(y, "y", self.n_cond, align=4) if self.n_cond else None
         B = x.shape[0] if batch_rows is None else int(batch_rows)
         if batch_index is not None:
             if x.shape[0] < B * n_batches:

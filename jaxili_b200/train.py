@@ -182,6 +182,9 @@ class HostBatchPipeline:
         self._check(self.lib.mafb200_pipeline_capture(self._p))
         self.i = self.base = 0
         self._out = np.empty(8192, np.float32)
+        # pinned batches are copied asynchronously from where they lie, on the executor's own copy stream, which
+        # torch's caching host allocator knows nothing about: keep them alive until drain() has seen their copies
+        self._inflight = []
         trainer._packed = True
 
     def __del__(self):
@@ -219,9 +222,11 @@ class HostBatchPipeline:
             py, pin_y, ky = None, True, None
         if self.i - self.base >= 8192:
             raise RuntimeError("loss ring full: call drain() at least every 8192 steps")
+        pinned = pin_x and pin_y
         self._check(self.lib.mafb200_pipeline_submit(self._p, self._C.c_void_p(px),
-                                                     self._C.c_void_p(py) if py else None,
-                                                     1 if (pin_x and pin_y) else 0))
+                                                     self._C.c_void_p(py) if py else None, 1 if pinned else 0))
+        if pinned:
+            self._inflight.append((kx, ky))     # released in drain(), after the copies have completed
         self.i += 1
 
     def drain(self):
@@ -231,6 +236,7 @@ class HostBatchPipeline:
             self._p, self._C.c_void_p(self._out.ctypes.data), self._out.size, self._C.byref(n),
             self._C.c_void_p(self.t._gbuf[-4:-3].data_ptr())))     # where the plain step leaves its loss
         self.base = self.i
+        self._inflight.clear()                  # drain() returns after every submitted copy and step has finished
         return self._out[: n.value].copy()
 
 
