@@ -211,6 +211,12 @@ int mafb200_forward(mafb200_handle h, const float* params, const float* x, const
                     int64_t B, float* out_logp, float* out_u, float* out_logdet,
                     int32_t flags, void* stream);
 
+/* eval_step + eval_model's accumulation (jaxili/train.py:337-340, 453-487) on the device:
+   acc[0] += -sum_b log_prob(x_b | y_b), acc[1] += B (acc: 2 device floats, zeroed by the caller before the loop).
+   The size-weighted mean loss of a loader is acc[0] / acc[1], read once after the loop. */
+int mafb200_eval_accumulate(mafb200_handle h, const float* params, const float* x, const float* y,
+                            int64_t B, float* acc, int32_t flags, void* stream);
+
 /* out_loss[0] = -inv_global_B * sum_b log p(x_b|y_b); out_grad = d out_loss / d params
    (P floats, masked entries exactly 0).  If batch_index != NULL the batch is rows
    [(batch_index[0] % n_batches) * B, +B) of x / y (device-side batch selection for

@@ -68,6 +68,8 @@ SYMBOLS = {
                                      C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mafb200_set_wide_core": (C.c_int, [C.c_void_p, C.c_int32]),
     "mafb200_set_flow_kernel": (C.c_int, [C.c_void_p, C.c_int32]),
+    "mafb200_eval_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                          C.c_int32, C.c_void_p]),
     "mafb200_param_count": (C.c_int64, [C.c_void_p]),
     "mafb200_get_mask": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mafb200_query": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int32)] * 4),

@@ -97,6 +97,8 @@ struct mafb200_handle_s {
   float* w_zero = nullptr;      // [cap][K0] zeros (addend of that product)
   float* w_dy = nullptr;        // [cap][C]  conditioner gradient summed over the layers
   long long wcap_dy = 0;
+  float* eval_lp = nullptr;     // log_prob scratch of mafb200_eval_accumulate
+  long long eval_cap = 0;
   // optional CUDA-event bracket around the flow kernel alone (roofline measurement in bench.py)
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -970,6 +972,7 @@ int mafb200_destroy(mafb200_handle h) {
   cudaFree(h->w_o); cudaFree(h->w_u); cudaFree(h->w_gx); cudaFree(h->w_ld);
   cudaFree(h->w_g[0]); cudaFree(h->w_g[1]);
   cudaFree(h->w_g0); cudaFree(h->w_zero); cudaFree(h->w_dy);
+  cudaFree(h->eval_lp);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
@@ -1287,6 +1290,28 @@ int mafb200_log_prob(mafb200_handle h, const float* params, const float* x, cons
                      float* out_logp, int32_t flags, void* stream) {
   if (!out_logp) return fail("null argument");
   return mafb200_forward(h, params, x, y, B, out_logp, nullptr, nullptr, flags, stream);
+}
+
+// eval_step + the accumulation of eval_model (jaxili/train.py:337-340, 453-487) without leaving the device:
+// acc[0] += -sum_b log_prob(x_b | y_b), acc[1] += B.  The size-weighted mean over a loader is acc[0] / acc[1],
+// read once at the end of the loop.  The log_prob scratch grows on demand (not during graph capture).
+int mafb200_eval_accumulate(mafb200_handle h, const float* params, const float* x, const float* y, int64_t B,
+                            float* acc, int32_t flags, void* stream) {
+  if (!h || !acc) return fail("null argument");
+  if (B <= 0) return B == 0 ? 0 : fail("negative batch");
+  CU(cudaSetDevice(h->device));
+  if (B > h->eval_cap) {
+    cudaFree(h->eval_lp);
+    h->eval_lp = nullptr;
+    h->eval_cap = 0;
+    const long long cap = std::max<long long>(B, 4096);
+    CU(cudaMalloc(&h->eval_lp, (size_t)cap * 4));
+    h->eval_cap = cap;
+  }
+  if (mafb200_forward(h, params, x, y, B, h->eval_lp, nullptr, nullptr, flags, stream)) return 1;
+  eval_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(h->eval_lp, B, acc);
+  CU(cudaGetLastError());
+  return 0;
 }
 
 int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, const float* y, int64_t B,

@@ -218,6 +218,23 @@ clip_adam_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
   }
 }
 
+// Validation / test loop on the device (jaxili/train.py:453-487: size-weighted mean of the batch losses =
+// -sum(log_prob) / rows): acc[0] += -sum_b lp[b], acc[1] += B, one block, fixed summation order.
+__global__ void __launch_bounds__(1024) eval_sum_kernel(const float* __restrict__ lp, long long B, float* __restrict__ acc) {
+  __shared__ float wsum[32];
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < B; i += 1024) s -= lp[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 32; ++w) t += wsum[w];
+    acc[0] += t;
+    acc[1] += (float)B;
+  }
+}
+
 // FP32 FFMA throughput probe with the operand pattern of the register-tiled GEMM inner loops:
 // acc[j][i] = fma(a[i], w[j], acc[j][i]) on 16 independent accumulators, all-register operands.
 __global__ void ffma_peak_kernel(float* out, int iters, float seed) {

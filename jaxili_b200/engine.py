@@ -74,6 +74,19 @@ class MafEngine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _pc(self, params, packed_current, image="flow"):
+        """PACKED_CURRENT flag for a call on ``params``: honoured only when the handle's packed image (``flow``: the
+        weight images / masked copy, ``sample``: the sorted sampler image) was last written from this very buffer.
+        The image lives in the shared handle: a call with other parameters in between (another checkpoint, a
+        posterior built on an older state) re-packs it, and the next ``packed_current=True`` call on the trainer's
+        buffer must pack again instead of running on foreign weights."""
+        key = "_packed_from_" + image
+        ok = bool(packed_current) and getattr(self, key, None) == params.data_ptr()
+        setattr(self, key, params.data_ptr())
+        if self.wide and image == "sample":
+            setattr(self, "_packed_from_flow", params.data_ptr())     # the wide sampler runs on the masked copy
+        return _lib.PACKED_CURRENT if ok else 0
+
     def _chk(self, t, name, cols=None, align=16):
         if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise TypeError(f"{name} must be a contiguous float32 CUDA tensor")
@@ -111,6 +124,18 @@ class MafEngine:
         """Wide path GEMM core: "tf32" (tcgen05, default) or "ffma" (FP32, exact)."""
         _lib.check(self.lib.mafb200_set_wide_core(self._h, {"ffma": 0, "tf32": 1}[core]))
 
+    def eval_accumulate(self, params, x, y, acc, packed_current=False):
+        """acc[0] += -sum(log_prob(x | y)), acc[1] += rows, on the device (eval_model's size-weighted mean)."""
+        px = self._chk(x, "x", self.n_in, align=4)
+        py = self._chk(y, "y", self.n_cond, align=4) if self.n_cond else None
+        B = x.shape[0]
+        if self.n_cond and y.shape[0] != B:
+            raise ValueError("x and y must have the same number of rows")
+        if B:
+            _lib.check(self.lib.mafb200_eval_accumulate(
+                self._h, self._chk(params, "params"), px, py, B, self._chk(acc, "acc", align=4),
+                self._pc(params, packed_current), self._stream()))
+
     def set_flow_kernel(self, mode):
         """Fused-kernel selection: "auto" (chain kernel for training, barrier-phased otherwise), "phased", "chain"."""
         _lib.check(self.lib.mafb200_set_flow_kernel(self._h, {"auto": 0, "phased": 1, "chain": 2}[mode]))
@@ -127,6 +152,11 @@ class MafEngine:
     # ------------------------------------------------------------------ hot path
     def pack(self, params):
         _lib.check(self.lib.mafb200_pack(self._h, self._chk(params, "params"), self._stream()))
+        self._packed_from_flow = params.data_ptr()
+
+    def invalidate_packed(self):
+        """Forget what the packed images were written from (call after changing parameters outside the library)."""
+        self._packed_from_flow = self._packed_from_sample = None
 
     def log_prob(self, params, x, y, out=None, packed_current=False):
         px = self._chk(x, "x", self.n_in, align=4)     # misaligned row tiles take the kernels' element-wise staging path
@@ -139,7 +169,7 @@ class MafEngine:
         if B:
             _lib.check(self.lib.mafb200_log_prob(
                 self._h, self._chk(params, "params"), px, py, B, self._chk(out, "out"),
-                _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
+                self._pc(params, packed_current), self._stream()))
         return out
 
     def forward(self, params, x, y, packed_current=False):
@@ -152,7 +182,7 @@ class MafEngine:
         if B:
             _lib.check(self.lib.mafb200_forward(
                 self._h, self._chk(params, "params"), px, py, B, None, self._chk(u, "u"),
-                self._chk(ld, "ld"), _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
+                self._chk(ld, "ld"), self._pc(params, packed_current), self._stream()))
         return u, ld
 
     def inverse(self, params, u, y, packed_current=False):
@@ -167,7 +197,7 @@ class MafEngine:
         if N:
             _lib.check(self.lib.mafb200_inverse(
                 self._h, self._chk(params, "params"), pu, py, N, self._chk(x, "x"),
-                self._chk(ld, "ld"), _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
+                self._chk(ld, "ld"), self._pc(params, packed_current, "sample"), self._stream()))
         return x, ld
 
     def log_prob_grad_y(self, params, x, y, packed_current=False):
@@ -182,7 +212,7 @@ class MafEngine:
         if B:
             _lib.check(self.lib.mafb200_log_prob_grad_y(
                 self._h, self._chk(params, "params"), px, py, B, self._chk(lp, "lp"), self._chk(dy, "dy"),
-                _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
+                self._pc(params, packed_current), self._stream()))
         return lp, dy
 
     def hmc_trajectory(self, params, x_rep, state, n_steps, packed_current=False):
@@ -206,7 +236,7 @@ class MafEngine:
             setattr(st, name, t.data_ptr())
         _lib.check(self.lib.mafb200_hmc_trajectory(
             self._h, self._chk(params, "params"), px, n, C.byref(st), int(n_steps),
-            _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
+            self._pc(params, packed_current), self._stream()))
 
     # ---- data parallel over NVLink peer memory
     def dp_init(self, rank, world):
@@ -256,7 +286,7 @@ class MafEngine:
         _lib.check(self.lib.mafb200_loss_grad(
             self._h, self._chk(params, "params"), px, py, B, inv, bi, int(n_batches),
             None if dp_slot else self._chk(out_loss, "out_loss"), None if dp_slot else self._chk(out_grad, "out_grad"),
-            (_lib.PACKED_CURRENT if packed_current else 0) | (_lib.DP_SLOT if dp_slot else 0), self._stream()))
+            (self._pc(params, packed_current)) | (_lib.DP_SLOT if dp_slot else 0), self._stream()))
 
     @staticmethod
     def make_opt_desc(lr=1e-3, warmup=0.0, decay_steps=1e9, clip=5.0, b1=0.9, b2=0.999, eps=1e-8,
@@ -275,6 +305,7 @@ class MafEngine:
         done, ``inv_global_b`` = 1 / global batch); the exchange happens inside the tail kernel."""
         if step.dtype != torch.int32 or not step.is_cuda:
             raise TypeError("step must be an int32 CUDA tensor")
+        self._packed_from_sample = None        # the update refreshes the flow images only
         px = self._chk(x, "x", self.n_in, align=4)     # misaligned row tiles take the kernels' element-wise staging path
         py = self._chk(y, "y", self.n_cond, align=4) if self.n_cond else None
         B = x.shape[0] if batch_rows is None else int(batch_rows)
@@ -290,10 +321,11 @@ class MafEngine:
             self._chk(out_loss, "out_loss"), self._chk(out_grad, "out_grad"),
             self._chk(m, "m") if m is not None else None, self._chk(v, "v") if v is not None else None,
             C.c_void_p(step.data_ptr()), C.byref(opt),
-            (_lib.PACKED_CURRENT if packed_current else 0) | (_lib.DP_SLOT if dp_slot else 0), self._stream()))
+            (self._pc(params, packed_current)) | (_lib.DP_SLOT if dp_slot else 0), self._stream()))
 
     def clip_adam(self, params, grad, m, v, step, opt, norm_current=False):
         """In-place optax-chain update; ``step`` is an int32 CUDA tensor (the optax count)."""
+        self._packed_from_sample = None        # the update refreshes the flow images only
         if step.dtype != torch.int32 or not step.is_cuda:
             raise TypeError("step must be an int32 CUDA tensor")
         _lib.check(self.lib.mafb200_clip_adam(
@@ -315,7 +347,7 @@ class MafEngine:
             _lib.check(self.lib.mafb200_sample_from_noise(
                 self._h, self._chk(params, "params"), pu,
                 self._chk(y_obs, "y_obs", align=4) if self.n_cond else None, n_obs, int(rows_per_obs), N,
-                self._chk(out, "out"), _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
+                self._chk(out, "out"), self._pc(params, packed_current, "sample"), self._stream()))
         return out
 
     def sample_philox(self, params, N, y_obs, seed=0, row_offset=0, rows_per_obs=None, out=None,
@@ -330,7 +362,7 @@ class MafEngine:
             _lib.check(self.lib.mafb200_sample_philox(
                 self._h, self._chk(params, "params"), int(seed) & (2**64 - 1), int(row_offset),
                 self._chk(y_obs, "y_obs", align=4) if self.n_cond else None, n_obs, int(rows_per_obs), int(N),
-                self._chk(out, "out"), _lib.PACKED_CURRENT if packed_current else 0, self._stream()))
+                self._chk(out, "out"), self._pc(params, packed_current, "sample"), self._stream()))
         return out
 
 

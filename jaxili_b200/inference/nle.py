@@ -27,6 +27,12 @@ class NLE(NPE):
 
     def _stats(self, z_score_theta, z_score_x):
         """jaxili/inference/nle.py:323-341: Standardizer on theta (conditioner), ScalarAffine on x."""
+        if getattr(self, "_resident", False):      # statistics on the device: population std, FP32
+            ds = self._train_dataset
+            st = lambda t: (t.mean(0).cpu().numpy(), t.std(0, unbiased=False).cpu().numpy())
+            shift, scale = st(ds.x) if z_score_x else (np.zeros(self._dim_params, np.float32),
+                                                       np.ones(self._dim_params, np.float32))
+            return shift, scale, (Standardizer(*st(ds.theta)) if z_score_theta else Identity())
         if z_score_theta:
             standardizer = Standardizer(np.mean(self._train_dataset.theta, axis=0, dtype=np.float32),
                                         np.std(self._train_dataset.theta, axis=0, dtype=np.float32))

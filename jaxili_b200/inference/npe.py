@@ -93,14 +93,30 @@ class NPE:
     def _dims(self, theta, x):
         return theta.shape[1], x.shape[1]   # NPE: density over theta, conditioned on x
 
-    def append_simulations(self, theta, x, train_test_split: Iterable[float] = [0.7, 0.2, 0.1], key=None):
-        """jaxili/inference/npe.py:220-294."""
+    def append_simulations(self, theta, x, train_test_split: Iterable[float] = [0.7, 0.2, 0.1], key=None,
+                           resident: bool = False, device=None):
+        """jaxili/inference/npe.py:220-294.  ``resident=True`` (not in the reference): the simulation set is
+        uploaded once, split and z-scored on the GPU and served by device-side loaders."""
         theta, x, num_sims = validate_theta_x(theta, x)
         if self.verbose:
             print("[!] Inputs are valid.")
             print(f"[!] Appending {num_sims} simulations to the dataset.")
         self._dim_params, self._dim_cond = self._dims(theta, x)
         self._num_sims = num_sims
+        self._resident = bool(resident)
+        if resident:
+            from ..train import split_resident
+            tr, va, te = split_resident(theta, x, list(train_test_split), key, device)
+            self.set_dataset(tr, type="train")
+            self.set_dataset(va, type="val")
+            self.set_dataset(te, type="test")
+            if self.verbose:
+                print("[!] Dataset split into training, validation and test sets (GPU-resident).")
+                print(f"[!] Training set: {len(tr)} simulations.")
+                print(f"[!] Validation set: {len(va)} simulations.")
+                if te is not None:
+                    print(f"[!] Test set: {len(te)} simulations.")
+            return self
         train_idx, val_idx, test_idx = split_indices(num_sims, list(train_test_split), key)
         self.set_dataset(NDEDataset(theta[train_idx], x[train_idx]), type="train")
         self.set_dataset(NDEDataset(theta[val_idx], x[val_idx]), type="val")
@@ -127,6 +143,16 @@ class NPE:
         batch_size = kwargs.get("batch_size", 128)
         if self.verbose:
             print(f"[!] Creating DataLoaders with batch_size {batch_size}.")
+        if getattr(self, "_resident", False):
+            # same semantics as utils.create_data_loader: the train loader reshuffles every epoch (seed 42) and
+            # drops the last partial batch, validation / test loaders run in order and keep it
+            from ..train import ResidentLoader
+            mk = lambda ds, tr: ResidentLoader(ds.theta, ds.x, batch_size, shuffle=tr, drop_last=tr,
+                                               seed=kwargs.get("seed", 42), device=ds.theta.device)
+            self._train_loader = mk(self._train_dataset, True)
+            self._val_loader = mk(self._val_dataset, False)
+            self._test_loader = None if self._test_dataset is None else mk(self._test_dataset, False)
+            return
         if self._test_dataset is None:
             self._train_loader, self._val_loader = create_data_loader(
                 self._train_dataset, self._val_dataset, train=train, **kwargs)
@@ -140,6 +166,12 @@ class NPE:
         population std of the train split in FP32 (jaxili/inference/npe.py:383-399)."""
         shift = np.zeros(self._dim_params, np.float32)
         scale = np.ones(self._dim_params, np.float32)
+        if getattr(self, "_resident", False):      # statistics on the device: population std, FP32
+            ds = self._train_dataset
+            st = lambda t: (t.mean(0).cpu().numpy(), t.std(0, unbiased=False).cpu().numpy())
+            if z_score_theta:
+                shift, scale = st(ds.theta)
+            return shift, scale, (Standardizer(*st(ds.x)) if z_score_x else Identity())
         if z_score_theta:
             shift = np.mean(self._train_dataset.theta, axis=0, dtype=np.float32)
             scale = np.std(self._train_dataset.theta, axis=0, dtype=np.float32)

@@ -120,6 +120,42 @@ class ResidentLoader:
             yield [theta[s], x[s]]
 
 
+class ResidentDataset:
+    """A split of a GPU-resident simulation set: ``theta`` / ``x`` are device tensors."""
+
+    def __init__(self, theta, x):
+        self.theta, self.x = theta, x
+
+    def __len__(self):
+        return self.theta.shape[0]
+
+    def __getitem__(self, idx):
+        return self.theta[idx], self.x[idx]
+
+
+def split_resident(theta, x, train_test_split, key, device=None):
+    """On-device random split with the reference's size arithmetic (jaxili/inference/npe.py:255-286: ``int()`` of
+    the cumulative fractions): one upload of the whole simulation set, a device permutation seeded from ``key``,
+    three gathers.  Returns (train, val, test-or-None) ``ResidentDataset``s."""
+    from .model import key_to_seed
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    th = torch.as_tensor(theta, dtype=torch.float32).to(device)
+    xx = torch.as_tensor(x, dtype=torch.float32).to(device)
+    n = th.shape[0]
+    fr = list(train_test_split)
+    if len(fr) not in (2, 3):
+        raise ValueError("train_test_split should have 2 or 3 elements.")
+    assert abs(sum(fr) - 1.0) < 1e-6, "The sum of the split fractions should be 1."
+    if key is None:
+        key = np.random.randint(0, 1000)
+    gen = torch.Generator(device=device).manual_seed(key_to_seed(key) % (2**63))
+    perm = torch.randperm(n, generator=gen, device=device)
+    n_tr = int(fr[0] * n)
+    n_tv = int((fr[0] + fr[1]) * n)
+    parts = [perm[:n_tr], perm[n_tr:n_tv], perm[n_tv:] if len(fr) == 3 else None]
+    return tuple(None if p is None else ResidentDataset(th[p].contiguous(), xx[p].contiguous()) for p in parts)
+
+
 def _capture(body, stream):
     """Capture ``body()`` (library launches only) into a CUDA graph.  Relaxed capture mode and a collected,
     paused garbage collector: an unrelated object dying mid-capture (a pinned buffer, another graph) would
@@ -404,6 +440,13 @@ class TrainerModule:
         raise NotImplementedError(
             "the fused backward implements loss_nll_npe / loss_nll_nle; other losses have no gradient here")
 
+    def _nll_loss(self):
+        try:
+            self._batch_xy([None, None])
+            return True
+        except NotImplementedError:
+            return False
+
     def create_functions(self):
         """jaxili/train.py:317-342."""
         def train_step(state: TrainState, batch: Any):
@@ -488,7 +531,11 @@ class TrainerModule:
         torch.cuda.current_stream(eng.device).wait_stream(s)
         self._packed = True
         self._graph = graph
-        return graph.replay
+
+        def step():
+            graph.replay()
+        step.check = self._check_dp      # call at a host sync point: raises if a peer rank went missing
+        return step
 
     # ------------------------------------------------------------------ loops
     def train_model(self, train_loader: Iterator, val_loader: Iterator, test_loader: Optional[Iterator] = None,
@@ -547,6 +594,7 @@ class TrainerModule:
                 metrics["train/" + key] = metrics["train/" + key] + step_metrics[key] / num_train_steps
         metrics = {key: float(metrics[key].item()) if hasattr(metrics[key], "item") else float(metrics[key])
                    for key in metrics}
+        self._check_dp()
         metrics["epoch_time"] = time.time() - start_time
         return metrics
 
@@ -594,6 +642,9 @@ class TrainerModule:
                 if pipe is not None:
                     total += float(pipe.drain().sum())
                 pipe = self.host_pipeline(rows)
+                eng = self.model.engine()
+                if getattr(eng, "_packed_from_flow", None) != pipe.flat.data_ptr():
+                    eng.pack(pipe.flat)          # another parameter set was packed into the handle in between
                 pipe.fence()
             if pipe.i - pipe.base >= 8192:
                 total += float(pipe.drain().sum())
@@ -601,13 +652,34 @@ class TrainerModule:
             n += 1
         if pipe is not None:
             total += float(pipe.drain().sum())
-            if pipe.peer and self.model.engine().dp_error():
-                raise RuntimeError("data-parallel exchange timed out: a peer rank did not reach the step "
-                                   "(its process died or stalled for longer than the exchange time-out)")
+        self._check_dp()
         return {"train/loss": total / max(num_train_steps, 1), "epoch_time": time.time() - start_time}
 
+    def _check_dp(self):
+        """Raise when the peer-memory gradient exchange lost a rank (the kernels then leave params / m / v / step
+        untouched and report NaN losses; the error word is read at the loops' existing host syncs)."""
+        _, world = parallel.world_info()
+        if world > 1 and self.model.engine().dp_error():
+            raise RuntimeError("data-parallel exchange timed out: a peer rank did not reach the step "
+                               "(its process died or stalled for longer than the exchange time-out)")
+
     def eval_model(self, data_loader: Iterator, log_prefix: Optional[str] = "") -> Dict[str, Any]:
-        """jaxili/train.py:453-487: size-weighted mean over the batches."""
+        """jaxili/train.py:453-487: size-weighted mean over the batches.  With the stock eval_step and an NLL loss
+        the whole loop stays on the device: every batch adds -sum(log_prob) and its row count to two device
+        scalars (mafb200_eval_accumulate), read once at the end -- the reference's single ``.item()``."""
+        if type(self).create_functions is TrainerModule.create_functions and self._nll_loss():
+            eng = self.model.engine()
+            acc = torch.zeros(2, dtype=torch.float32, device=eng.device)
+            flat = self.model.flat_params(self.state.params)
+            first = True
+            for batch in data_loader:
+                xd, yd = self._batch_xy(batch)
+                x = self._to_device(xd, eng.n_in, "ex")
+                y = self._to_device(yd, eng.n_cond, "ey") if eng.n_cond else None
+                eng.eval_accumulate(flat, x, y, acc, packed_current=not first)
+                first = False
+            a = acc.cpu().numpy()
+            return {(log_prefix + "loss"): float(a[0] / max(a[1], 1.0))}
         metrics = defaultdict(float)
         num_elements = 0
         for batch in data_loader:

@@ -325,3 +325,82 @@ def test_errors_like_reference():
         ConditionalMAF(2, 2, 2, [8], activation="not_an_activation")
     with pytest.raises(ValueError):
         ConditionalMAF(1, 2, 2, [8], activation="relu", seed=1).engine()   # n_in=1: randint(0,0) in jaxili
+
+
+def test_resident_loader_and_on_device_split(tmp_path):
+    """GPU-resident simulation set, split / z-scored / shuffled on the device.  Split sizes follow the
+    reference's int() arithmetic (jaxili/inference/npe.py:269-280), the loaders keep create_data_loader's
+    semantics (jaxili/utils.py:72-81), and training runs on batches that are views of the resident tensors --
+    including a width (3) and batch size (50) whose row slices are not 16-byte aligned."""
+    from jaxili_b200.inference import NPE
+    from jaxili_b200.train import ResidentLoader
+    rng = np.random.default_rng(3)
+    n = 4001
+    theta = rng.uniform(-1, 1, size=(n, 3)).astype(np.float32)
+    x = (theta @ rng.standard_normal((3, 5)).astype(np.float32) + 0.2 * rng.standard_normal((n, 5))).astype(np.float32)
+    inf = NPE(verbose=False, model_hparams=dict(n_layers=3, layers=[32, 32], activation="relu", use_reverse=True, seed=42))
+    inf.append_simulations(theta, x, train_test_split=[0.7, 0.2, 0.1], key=5, resident=True)
+    tr, va, te = inf._train_dataset, inf._val_dataset, inf._test_dataset
+    assert (len(tr), len(va), len(te)) == (int(0.7 * n), int(0.9 * n) - int(0.7 * n), n - int(0.9 * n))
+    assert tr.theta.is_cuda and tr.x.is_cuda
+    # the three parts are a partition of the simulation set (rows kept together)
+    rows = torch.cat([torch.cat([d.theta, d.x], 1) for d in (tr, va, te)]).cpu().numpy()
+    full = np.concatenate([theta, x], 1)
+    assert rows.shape == full.shape
+    assert np.array_equal(rows[np.lexsort(rows.T[::-1])], full[np.lexsort(full.T[::-1])])
+    # same key -> same split; statistics = population mean / std of the train part
+    inf2 = NPE(verbose=False).append_simulations(theta, x, key=5, resident=True)
+    assert torch.equal(inf2._train_dataset.theta, tr.theta)
+    shift, scale, stdz = inf._stats(True, True)
+    npt.assert_allclose(shift, tr.theta.cpu().numpy().mean(0), rtol=1e-5, atol=1e-6)
+    npt.assert_allclose(scale, tr.theta.cpu().numpy().std(0), rtol=1e-5, atol=1e-6)
+    # loader semantics
+    inf._create_data_loader(batch_size=50)
+    tl, vl = inf._train_loader, inf._val_loader
+    assert isinstance(tl, ResidentLoader) and len(tl) == len(tr) // 50 and len(vl) == -(-len(va) // 50)
+    e1 = torch.cat([b[0] for b in tl]); e2 = torch.cat([b[0] for b in tl])
+    assert e1.shape[0] == len(tl) * 50 and not torch.equal(e1, e2)              # reshuffled every epoch
+    key = lambda t: t[:, 0].sort().values
+    sub = torch.isin(key(e1), key(tr.theta)).all()                              # every batch row is a train row
+    assert bool(sub)
+    tl_b = ResidentLoader(tr.theta, tr.x, 50, shuffle=True, drop_last=True, seed=42)
+    assert torch.equal(torch.cat([b[0] for b in tl_b]), e1)                     # seeded: same first epoch
+    assert torch.equal(torch.cat([b[0] for b in vl]), va.theta)                 # validation: in order, last batch kept
+    # training on the resident loaders (device batches, misaligned slices: 50 rows x 3 floats = 600 B)
+    metrics, est = inf.train(training_batch_size=50, learning_rate=2e-3, num_epochs=6, checkpoint_path=str(tmp_path / "ck"))
+    assert np.isfinite(metrics["train/loss"]) and np.isfinite(metrics["val/loss"]) and "test/loss" in metrics
+    assert est.log_prob(theta[:7], x[:7]).shape == (7,)
+
+
+def test_eval_model_on_device_equals_host_loop():
+    """eval_model's size-weighted mean (jaxili/train.py:453-487) accumulated on the device equals the
+    host loop over eval_step, ragged last batch included."""
+    from jaxili_b200.inference import NPE
+    theta, x = _sim(3000, seed=9)
+    inf = NPE(verbose=False).append_simulations(theta, x, key=1)
+    inf._create_data_loader(batch_size=128)
+    inf.create_trainer({"lr": 1e-3, "optimizer_name": "adam", "gradient_clip": 5.0, "warmup": 0.1, "weight_decay": 0.0},
+                       logger_params={"base_log_dir": "/tmp/jaxili_b200_eval_test"})
+    tr = inf.trainer
+    tr.init_optimizer(3, len(inf._train_loader))
+    tr.train_epoch(inf._train_loader)
+    dev = tr.eval_model(inf._val_loader, log_prefix="val/")["val/loss"]
+    tot, cnt = 0.0, 0
+    for batch in inf._val_loader:
+        m = tr.eval_step(tr.state, batch)
+        tot += float(m["loss"].item()) * batch[0].shape[0]
+        cnt += batch[0].shape[0]
+    assert abs(dev - tot / cnt) < 1e-5 * max(1.0, abs(dev))
+    # a call on OTHER parameters re-packs the shared handle; the next training step must not run on them
+    eng = tr.model.engine()
+    other = tr.state.params.flat.clone().mul_(0.5)
+    xb, yb = tr._batch_xy(next(iter(inf._val_loader)))
+    eng.log_prob(other, torch.tensor(xb, device=eng.device), torch.tensor(yb, device=eng.device))
+    before = tr.state.params.flat.clone()
+    ref_loss = tr.eval_model(inf._val_loader)["loss"]
+    assert abs(ref_loss - dev) < 1e-5 * max(1.0, abs(dev))                      # eval packs the trainer's weights again
+    eng.log_prob(other, torch.tensor(xb, device=eng.device), torch.tensor(yb, device=eng.device))
+    tr.stream_host_batches = False
+    tr.state, m = tr.train_step(tr.state, next(iter(inf._train_loader)))        # packed_current=True would be stale here
+    assert abs(float(m["loss"].item()) - ref_loss) < 0.5                        # loss of the trainer's weights, not of `other`
+    assert not torch.equal(before, tr.state.params.flat)
