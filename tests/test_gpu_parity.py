@@ -157,6 +157,21 @@ def test_sample_from_noise_matches_oracle(name, N, rev, act):
     assert rel_err(out, ref) < 2e-5
 
 
+def test_sample_c4_parity_slice():
+    """the c4 parity slice -- 65 536 supplied base-noise rows over 64 observations (1 024 each)
+    through the inversion kernel against the oracle's D-pass inverse, trained-scale weights."""
+    n_obs, per, = 64, 1024
+    spec, flat, std, x, y = make_case(CONFIGS["c2"], n_obs, seed=16)
+    eng = _engine(spec, std)
+    u = np.random.default_rng(17).standard_normal((n_obs * per, spec.n_in)).astype(np.float32)
+    out = eng.sample_from_noise(_t(flat), _t(u), _t(y), rows_per_obs=per).cpu().numpy()
+    f64 = flat.astype(np.float64)
+    ref = np.concatenate([onp.nde_sample_from_noise(spec, f64, std, u[i * per:(i + 1) * per].astype(np.float64), y[i])
+                          for i in range(n_obs)])
+    assert np.isfinite(out).all()
+    assert rel_err(out, ref) < 2e-5
+
+
 def test_sample_roundtrip_and_clamp():
     """forward(sample(u)) == u (jaxili/tests/test_nn.py:35-41 invariant), 1e-5."""
     spec, flat, std, x, y = make_case(CONFIGS["c2"], 1, seed=8, scale=0.05)
