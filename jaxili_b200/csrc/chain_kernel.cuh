@@ -227,7 +227,6 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
   constexpr int UL = NLIN > 0 ? NLIN : 1;                    // unroll factor of the loops over the linears
   const int n_lin = NLIN > 0 ? NLIN : P.n_lin;
   const int Rt = A.Rt;
-  const long long row_base = A.batch_index ? (long long)(A.batch_index[0] % A.n_batches) * A.B : 0;
   const int grid = gridDim.x;
   const int my_n = (A.n_tiles - (int)blockIdx.x + grid - 1) / grid;
   const int per_tile = BWD ? 2 * L : L;
@@ -269,6 +268,10 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
     float4* z = reinterpret_cast<float4*>(sm);
     for (int idx = P.o_xin / 4 + tid; idx < n4; idx += NT) z[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  // everything above is independent of the preceding kernel in the stream (the optimiser step that rewrites the
+  // weight images and bumps the step counter): under programmatic dependent launch it overlaps that kernel's tail
+  griddep_wait();
+  const long long row_base = A.batch_index ? (long long)(A.batch_index[0] % A.n_batches) * A.B : 0;
   __syncthreads();
   float* const cst = sm + P.o_cst;   // [shift D][inv_scale D][mean C][std C]
   for (int idx = tid; idx < 2 * D + 2 * C; idx += NT) cst[idx] = A.stdc[idx];

@@ -50,6 +50,11 @@ __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// programmatic dependent launch (PDL): wait for the preceding grid in the stream (no-op without the launch attribute);
+// allow the following grid to start launching
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- small vector loads / stores
 __device__ __forceinline__ void ldv(float (&d)[4], const float* p) {
   const float4 v = *reinterpret_cast<const float4*>(p);

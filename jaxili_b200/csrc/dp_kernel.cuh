@@ -154,6 +154,16 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
     }
   };
   tstamp(0);
+  // operands of the update: independent of the flow kernel, fetched before the programmatic-dependency wait
+  float pv = 0.f, mv = 0.f, vv = 0.f;
+  unsigned char mk = 0;
+  if (p == 0 && idx < P.P) {
+    pv = params[idx];
+    mk = mask[idx];
+    if (O.kind != 1) { mv = m[idx]; vv = v[idx]; }
+  }
+  griddep_launch_dependents();     // the next step's flow kernel may start launching (it waits for this grid's end)
+  griddep_wait();                  // the flow kernel's partial gradients and step counter are complete
   const int t = step[0];
   // DP: the locally reduced gradient is PUSHED into every rank's receive area of the coming epoch
   // (= count + 1; parity alternates): remote stores are fire-and-forget, the later sum reads local memory only
@@ -167,14 +177,6 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
     for (int g = p; g < G; g += RED_PARTS) s += src[(size_t)g * P.P];
   }
   red[p][i] = s;
-  // operands of the update, fetched while the partial sums are in flight
-  float pv = 0.f, mv = 0.f, vv = 0.f;
-  unsigned char mk = 0;
-  if (p == 0 && idx < P.P) {
-    pv = params[idx];
-    mk = mask[idx];
-    if (O.kind != 1) { mv = m[idx]; vv = v[idx]; }
-  }
   __syncthreads();
   float g = 0.f;
   if (p == 0) {
