@@ -65,6 +65,7 @@ struct mafb200_handle_s {
   float* partial = nullptr;     // [n_sm][P]
   float* partial_loss = nullptr;
   float* normpart = nullptr;
+  float* normsum = nullptr;     // [1] sum of the partials (large models: summed once, not by every block)
   unsigned int* done_counter = nullptr;
   unsigned long long* grid_bar = nullptr;   // ticket counter of step_tail_kernel's grid barrier
   int tail_ok = -1;             // step_tail_kernel co-residency (-1: not probed yet)
@@ -623,8 +624,8 @@ int wide_chunk(mafb200_handle h, const float* x, const float* y, long long rows,
         g.k_chunk = k_chunk;
         if (wide_gemm<false, false, EPI_ATOMIC_MASK>(h, g, relu, (int)((rows + k_chunk - 1) / k_chunk), st)) return 1;
         if (i == n_lin - 1) {   // hidden levels get their bias gradient from the producing GEMM's epilogue
-          const int rpb = 512;
-          wide_colsum_kernel<<<dim3((ln.N + 127) / 128, (unsigned)((rows + rpb - 1) / rpb)), 128, 0, st>>>(
+          const int rpb = 256;
+          wide_colsum_kernel<<<dim3((ln.N + 31) / 32, (unsigned)((rows + rpb - 1) / rpb)), 256, 0, st>>>(
               G, rows, ln.N, rpb, gl + ln.pb_off);
           CU(cudaGetLastError());
         }
@@ -882,6 +883,7 @@ int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shi
   h->n_norm = (P.P + RED_IDX - 1) / RED_IDX;
   CUH(cudaMalloc(&h->normpart, h->n_norm * 4));
   CUH(cudaMemset(h->normpart, 0, h->n_norm * 4));
+  CUH(cudaMalloc(&h->normsum, 4));
   CUH(cudaMalloc(&h->done_counter, 4));
   CUH(cudaMemset(h->done_counter, 0, 4));
   CUH(cudaMalloc(&h->grid_bar, 8));
@@ -981,6 +983,7 @@ int mafb200_destroy(mafb200_handle h) {
   cudaFree(h->partial);
   cudaFree(h->partial_loss);
   cudaFree(h->normpart);
+  cudaFree(h->normsum);
   cudaFree(h->done_counter);
   cudaFree(h->grid_bar);
   for (int r = 0; r < h->dp_world; ++r)
@@ -1588,7 +1591,15 @@ int mafb200_clip_adam(mafb200_handle h, float* params, const float* grad, float*
   }
   OptArgs O{opt->lr, opt->warmup, opt->decay_steps, opt->init_factor, opt->end_factor, opt->b1, opt->b2,
             opt->eps, opt->clip, opt->weight_decay, opt->kind};
-  clip_adam_kernel<<<h->n_norm, RED_IDX, 0, st>>>(P, O, params, grad, m, v, step, h->normpart, h->n_norm,
+  const float* npart = h->normpart;
+  int n_part = h->n_norm;
+  if (n_part > 2048) {   // wide models: tens of thousands of partials -- sum them once
+    sum_partials_kernel<<<1, 1024, 0, st>>>(h->normpart, h->n_norm, h->normsum);
+    CU(cudaGetLastError());
+    npart = h->normsum;
+    n_part = 1;
+  }
+  clip_adam_kernel<<<h->n_norm, RED_IDX, 0, st>>>(P, O, params, grad, m, v, step, npart, n_part,
                                                   h->mask, h->wide ? h->wm : h->wimg, h->wide ? 1 : 0,
                                                   h->done_counter, nullptr);
   CU(cudaGetLastError());

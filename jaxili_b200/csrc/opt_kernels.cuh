@@ -141,6 +141,22 @@ sqnorm_kernel(const float* __restrict__ grad, int P, float* __restrict__ normpar
   }
 }
 
+// sum of the squared-norm partials in a fixed order (one block): large models have tens of thousands of partials,
+// which every block of clip_adam_kernel would otherwise re-read
+__global__ void __launch_bounds__(1024) sum_partials_kernel(const float* __restrict__ part, int n, float* __restrict__ out) {
+  __shared__ float wsum[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) s += part[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 32; ++w) t += wsum[w];
+    out[0] = t;
+  }
+}
+
 // optax.warmup_cosine_decay_schedule evaluated in FP32 at integer count t
 __device__ __forceinline__ float lr_schedule(const OptArgs& o, int t) {
   const float tf = (float)t;

@@ -305,16 +305,35 @@ __global__ void wide_bwd_elem_kernel(WideCommon w, const float* __restrict__ gu,
   gxdir[idx] = gv * s;
 }
 
-// bias gradient: column sums of G [M x N] accumulated into db[N]
-__global__ void wide_colsum_kernel(const float* __restrict__ G, long long M, int N, int rows_per_block,
-                                   float* __restrict__ db) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// bias gradient: column sums of G [M x N] accumulated into db[N].  Block = 256 threads = 8 row lanes x 32 columns:
+// a warp reads 32 consecutive columns of one row (coalesced), the 8 warps stride the block's rows, the partial
+// sums meet in shared memory and leave as one reduction per column and block.
+__global__ void __launch_bounds__(256) wide_colsum_kernel(const float* __restrict__ G, long long M, int N,
+                                                          int rows_per_block, float* __restrict__ db) {
+  __shared__ float part[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = min(M, r0 + rows_per_block);
-  float s = 0.f;
-  for (long long r = r0; r < r1; ++r) s += G[r * N + n];
-  atomicAdd(&db[n], s);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (n < N) {
+    long long r = r0 + w;
+    for (; r + 24 < r1; r += 32) {     // four independent loads in flight per thread
+      s0 += G[r * N + n];
+      s1 += G[(r + 8) * N + n];
+      s2 += G[(r + 16) * N + n];
+      s3 += G[(r + 24) * N + n];
+    }
+    for (; r < r1; r += 8) s0 += G[r * N + n];
+  }
+  part[w][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (w == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][lane];
+    atomicAdd(&db[n], t);
+  }
 }
 
 // mask-folded copy of the parameters in the same flat layout (the wide path's "image")
