@@ -346,7 +346,7 @@ maf_chain_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArg
   // layer step sq = ti * L + (L - 1 - k) alternates between the two gradient-buffer sets
   if (BWD && warp <= GW) {
     const int gw = warp - 1;
-    float* pg_cta = A.partial_grad + (size_t)blockIdx.x * P.P;
+    float* pg_cta = A.partial_grad + (size_t)blockIdx.x * P.pgs;
     const int total_steps = my_n * L;
     // flat list of 8x4 tiles over the linears of one layer, one tile per lane and round; a tile takes the strided
     // features k = kb + i * nKB (i < 8; k == K is the ones row = bias), n = nb + j * nNB (j < 4): the rows one

@@ -132,14 +132,14 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, bool syste
 }
 
 template <bool DP>
-__global__ void __launch_bounds__(RED_IDX * RED_PARTS, 2)   // two blocks per SM: all ceil(P/128) blocks co-resident
+__global__ void __launch_bounds__(RED_THREADS, 2)   // two blocks per SM: all ceil(P/128) blocks co-resident
 step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs O, const float* __restrict__ partial,
                  int G, const unsigned char* __restrict__ mask, float* __restrict__ grad,
                  const float* __restrict__ partial_loss, float* __restrict__ loss, float* __restrict__ normpart,
                  float* __restrict__ params, float* __restrict__ m, float* __restrict__ v, int* __restrict__ step,
                  float* __restrict__ wimg, unsigned long long* __restrict__ grid_bar,
                  const __grid_constant__ DpArgs a) {
-  __shared__ float red[RED_PARTS][RED_IDX];
+  __shared__ __align__(16) float red[RED_PARTS][RED_IDX];
   __shared__ float wsum[RED_IDX / 32];
   __shared__ float lsum[RED_IDX / 32];
   __shared__ float s_norm;
@@ -150,6 +150,7 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
     if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) {
       unsigned long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (k == 0) a.trace[7] = (long long)now - a.trace[6];   // previous tail's end -> this tail's start
       a.trace[k] = (long long)now;
     }
   };
@@ -170,13 +171,7 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
   const unsigned int epoch = (unsigned int)t + 1u;
   // index (in 64-bit words) of this rank's lane in a receive area of the epoch's parity
   const long long roff = DP ? ((long long)(epoch & 1u) * DP_MAX_WORLD + a.rank) * a.slot_floats : 0;
-  float s = 0.f;
-  if (idx < P.P) {
-    const float* src = partial + idx;
-#pragma unroll 4
-    for (int g = p; g < G; g += RED_PARTS) s += src[(size_t)g * P.P];
-  }
-  red[p][i] = s;
+  reduce_partials(partial, P.pgs, G, P.P, red);
   __syncthreads();
   float g = 0.f;
   if (p == 0) {
@@ -314,6 +309,13 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
   // every block read step[0] before the barrier
   if (blockIdx.x == 0 && i == 0 && !dp_fail) step[0] = t + 1;
   tstamp(6);
+#ifdef MAFB_CTA_TIMES
+  if (a.trace && threadIdx.x == 0) {   // debug: every block's exit time (trace + 900 is the base: slots 600..)
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    a.trace[-300 + (int)blockIdx.x] = (long long)now;
+  }
+#endif
 }
 
 }  // namespace mafb

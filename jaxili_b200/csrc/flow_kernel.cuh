@@ -389,7 +389,7 @@ maf_flow_kernel(const __grid_constant__ Plan P, const __grid_constant__ FlowArgs
     stamp(6);
 
     if (BWD) {
-      float* pg_cta = A.partial_grad + (size_t)blockIdx.x * P.P;
+      float* pg_cta = A.partial_grad + (size_t)blockIdx.x * P.pgs;
       const bool accum = ti > 0;
       for (int k = L - 1; k >= 0; --k) {
         const float* wimg_s = w_acquire(req++);

@@ -248,6 +248,7 @@ bool make_plan(const MafDesc& d, const int* dims, Plan& P, int occ) {
   P.img_floats = P.fwd_floats + P.bwd_floats;
   P.ppl = po;
   P.P = po * P.L;
+  P.pgs = r4(P.P);
   static const int Rs[] = {32, 16, 8, 4};
   for (int R : Rs) {
     if (occ == 2 && R > 16) continue;
@@ -284,6 +285,7 @@ void make_plan_dims_only(const MafDesc& d, const int* dims, Plan& P) {
   }
   P.ppl = po;
   P.P = po * P.L;
+  P.pgs = r4(P.P);
 }
 
 // ------------------------------------------------------------------ sampler planner + sorted positions
@@ -878,7 +880,10 @@ int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shi
     CUH(cudaMemset(h->wimg, 0, (size_t)P.L * P.img_floats * 4));
   }
   CUH(cudaMalloc(&h->stdc, (3 * P.D + 2 * P.C) * 4));
-  if (!h->wide) CUH(cudaMalloc(&h->partial, (size_t)2 * h->n_sm * P.P * 4));
+  if (!h->wide) {
+    CUH(cudaMalloc(&h->partial, (size_t)2 * h->n_sm * P.pgs * 4));
+    CUH(cudaMemset(h->partial, 0, (size_t)2 * h->n_sm * P.pgs * 4));
+  }
   CUH(cudaMalloc(&h->partial_loss, 2 * h->n_sm * 4));
   h->n_norm = (P.P + RED_IDX - 1) / RED_IDX;
   CUH(cudaMalloc(&h->normpart, h->n_norm * 4));
@@ -1381,7 +1386,7 @@ int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, con
   CU(cudaGetLastError());
   if (h->timing) CU(cudaEventRecord(h->ev1, st));
   const size_t sf = dp_slot_floats(P);
-  reduce_kernel<<<h->n_norm, RED_IDX * RED_PARTS, 0, st>>>(h->partial, grid, P.P, h->mask, out_grad,
+  reduce_kernel<<<h->n_norm, RED_THREADS, 0, st>>>(h->partial, P.pgs, grid, P.P, h->mask, out_grad,
                                                          h->partial_loss, out_loss, h->normpart,
                                                          dp_slot ? h->dp_step : nullptr, h->dp_sym,
                                                          h->dp_sym ? h->dp_sym + sf : nullptr);
@@ -1491,7 +1496,7 @@ int mafb200_train_step(mafb200_handle h, float* params, const float* x, const fl
   if (opt->decay_steps - opt->warmup <= 0.f) return fail("cosine_decay_schedule requires positive decay_steps");
   if (!h->wide && h->tail_ok < 0) {
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_tail_kernel<true>, RED_IDX * RED_PARTS, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_tail_kernel<true>, RED_THREADS, 0));
     int coop = 0;
     CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
     h->tail_ok = (coop && (long long)per_sm * h->n_sm >= h->n_norm) ? 1 : 0;
@@ -1563,7 +1568,7 @@ int mafb200_train_step(mafb200_handle h, float* params, const float* x, const fl
   const void* fn = dp ? (const void*)step_tail_kernel<true> : (const void*)step_tail_kernel<false>;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(h->n_norm);
-  cfg.blockDim = dim3(RED_IDX * RED_PARTS);
+  cfg.blockDim = dim3(RED_THREADS);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute at[2];

@@ -19,7 +19,9 @@ struct OptArgs {
 };
 
 constexpr int RED_IDX = 128;    // parameters per reduction block (181 blocks for the narrow configs: every SM busy)
-constexpr int RED_PARTS = 8;    // threads cooperating on one parameter
+constexpr int RED_PARTS = 8;    // partial sums per parameter (part p takes the CTAs g = p, p + 8, ...)
+constexpr int RED_THREADS = 32 * RED_PARTS;   // warp p = part p; lane q = parameters 4q .. 4q+3 of the block's 128
+constexpr int RED_BATCH = 10;   // 128-bit loads in flight per thread
 
 // fixed-order pairwise sum of the RED_PARTS partial sums of parameter i
 __device__ __forceinline__ float red_parts_sum(const float (&red)[RED_PARTS][RED_IDX], int i) {
@@ -71,9 +73,36 @@ __global__ void pack_kernel(const __grid_constant__ Plan P, const float* __restr
   write_image(P, wimg, idx, mask[idx] ? params[idx] : 0.f);
 }
 
-// block: RED_IDX * RED_PARTS threads.  normpart[blockIdx] = sum of grad^2 over the block.
-__global__ void __launch_bounds__(RED_IDX * RED_PARTS)
-reduce_kernel(const float* __restrict__ partial, int G, int P, const unsigned char* __restrict__ mask,
+// Part sums of the block's 128 parameters over the per-CTA partial gradients [G][stride]: warp p adds the rows
+// g = p, p + 8, ... in that order, four neighbouring parameters per lane with one 128-bit load per row (a warp reads
+// 512 contiguous bytes), RED_BATCH rows requested before the first add.  A step reads G * P * 4 bytes here (13.7 MB
+// at c2) out of L2: the loads in flight, not the adds, set the time.
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int stride, int G, int P,
+                                                float (&red)[RED_PARTS][RED_IDX]) {
+  const int q = threadIdx.x & 31, p = threadIdx.x >> 5;
+  const int i4 = blockIdx.x * RED_IDX + 4 * q;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i4 < P) {                                       // stride % 4 == 0 and stride >= P: the 128-bit read stays in the row
+    const float4* src = reinterpret_cast<const float4*>(partial + i4);
+    const size_t st4 = (size_t)(stride >> 2);
+    for (int g0 = p; g0 < G; g0 += RED_PARTS * RED_BATCH) {
+      float4 v[RED_BATCH];
+#pragma unroll
+      for (int u = 0; u < RED_BATCH; ++u) {
+        const int g = g0 + u * RED_PARTS;
+        if (g < G) v[u] = __ldcg(src + (size_t)g * st4);
+      }
+#pragma unroll
+      for (int u = 0; u < RED_BATCH; ++u)
+        if (g0 + u * RED_PARTS < G) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+  }
+  *reinterpret_cast<float4*>(&red[p][4 * q]) = s;
+}
+
+// block: RED_THREADS threads.  normpart[blockIdx] = sum of grad^2 over the block.
+__global__ void __launch_bounds__(RED_THREADS)
+reduce_kernel(const float* __restrict__ partial, int stride, int G, int P, const unsigned char* __restrict__ mask,
               float* __restrict__ grad, const float* __restrict__ partial_loss, float* __restrict__ loss,
               float* __restrict__ normpart, const int* __restrict__ dp_step, float* dp_slot0,
               float* dp_slot1) {
@@ -83,17 +112,11 @@ reduce_kernel(const float* __restrict__ partial, int G, int P, const unsigned ch
     grad = ((dp_step[0] + 1) & 1) ? dp_slot1 : dp_slot0;
     loss = grad + ((P + 3) & ~3);
   }
-  __shared__ float red[RED_PARTS][RED_IDX];
+  __shared__ __align__(16) float red[RED_PARTS][RED_IDX];
   __shared__ float wsum[RED_IDX / 32];
-  const int i = threadIdx.x % RED_IDX, p = threadIdx.x / RED_IDX;
+  const int i = threadIdx.x % RED_IDX, p = threadIdx.x / RED_IDX;   // after the part sums: one parameter per thread of group 0
   const int idx = blockIdx.x * RED_IDX + i;
-  float s = 0.f;
-  if (idx < P) {
-    const float* src = partial + idx;
-#pragma unroll 4
-    for (int g = p; g < G; g += RED_PARTS) s += src[(size_t)g * P];
-  }
-  red[p][i] = s;
+  reduce_partials(partial, stride, G, P, red);
   __syncthreads();
   if (p == 0) {
     float tot = 0.f;

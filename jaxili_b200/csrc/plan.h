@@ -27,6 +27,7 @@ struct Plan {
   int fwd_floats, bwd_floats;   // per-layer image parts (multiples of 4 floats)
   int img_floats;               // fwd_floats + bwd_floats
   int ppl, P;                   // params per layer, total
+  int pgs;                      // row stride of the per-CTA partial gradients (P rounded up to 4: 128-bit reads)
   // tiling
   int R, RP;                    // rows per tile, row pitch of feature-major buffers
   int threads;

@@ -37,10 +37,19 @@ for rep in range(6):
     for _ in range(50):
         step()
     e1.record(); torch.cuda.synchronize()
-    t = trace[900:907].cpu().numpy()
-    g_rows.append([e0.elapsed_time(e1) * 1e3 / 50] + [(t[k] - t[0]) / 1e3 for k in range(1, 7)])
+    t = trace[900:908].cpu().numpy()
+    g_rows.append([e0.elapsed_time(e1) * 1e3 / 50] + [(t[k] - t[0]) / 1e3 for k in range(1, 7)] + [t[7] / 1e3])
+    if os.environ.get("MAFB_CTA_TIMES") and rank == 0 and rep == 5:
+        # library built with MAFB_CTA_TIMES=1: the last flow launch's per-CTA stamps, relative to the tail's start
+        tr_ = trace.cpu().numpy()
+        n = 147
+        t_in, t_grad, t_chain = tr_[0:2 * n:2], tr_[1:2 * n:2], tr_[400:400 + n]
+        f = lambda a: "min %.2f max %.2f" % ((a.min() - t[0]) / 1e3, (a.max() - t[0]) / 1e3)
+        t_tail = tr_[600:600 + 181]
+        print("tail block exit", f(t_tail), "| previous tail's exits are overwritten: compare with column 'end'")
+        print("flow CTA entry", f(t_in), "| chain exit", f(t_chain), "| grad exit", f(t_grad), " (us, tail start = 0)")
 if rank == 0:
-    print("GRAPH mode: step_us | stage1 done, flags raised, peers seen, summed, barrier B, end")
+    print("GRAPH mode: step_us | stage1 done, flags raised, peers seen, summed, barrier B, end | previous tail end -> tail start")
     for r in g_rows:
         print("G " + " ".join(f"{v:8.2f}" for v in r))
 dist.barrier()
