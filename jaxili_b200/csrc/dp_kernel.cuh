@@ -114,36 +114,24 @@ __global__ void __launch_bounds__(RED_IDX) dp_allreduce_kernel(const __grid_cons
 // ---------------------------------------------------------------------------------------------------------
 // Whole tail of a training step in ONE launch: reduction of the per-CTA partial gradients (reduce_kernel),
 // [DP: one-shot exchange with the peers, as dp_allreduce_kernel], global norm, clip + schedule + Adam +
-// re-pack of the weight images (clip_adam_kernel).  The global norm needs every block's partial, so the
-// blocks meet at a grid barrier (two with DP: the rank's slot must be complete before its epoch flag is
-// raised); the kernel is launched cooperatively (all ceil(P/256) blocks co-resident: narrow models only)
-// and each parameter's gradient stays in the register of the thread that produced it across the barriers.
-__device__ __forceinline__ void grid_barrier(unsigned long long* bar, bool system_scope) {
-  // monotone 64-bit ticket counter (never reset, no wrap); one thread per block calls this after a
-  // __syncthreads(), which makes the block's earlier writes cumulative with its fence
-  if (system_scope) __threadfence_system();
-  else __threadfence();
-  const unsigned long long ticket = atomicAdd(bar, 1ull);
-  const unsigned long long target = (ticket / gridDim.x + 1ull) * gridDim.x;
-  unsigned long long seen;
-  do {
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(bar) : "memory");
-  } while (seen < target);
-}
-
+// re-pack of the weight images (clip_adam_kernel).  The global norm needs every block's partial: each block
+// publishes its partial as a 64-bit {value, launch epoch} word and polls everybody else's (one L2 round trip
+// instead of a grid barrier and a re-read); the kernel is launched cooperatively (all ceil(P/128) blocks
+// co-resident: narrow models only) and each parameter's gradient stays in the register of the thread that
+// produced it across the wait.
 template <bool DP>
 __global__ void __launch_bounds__(RED_THREADS, 2)   // two blocks per SM: all ceil(P/128) blocks co-resident
 step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs O, const float* __restrict__ partial,
                  int G, const unsigned char* __restrict__ mask, float* __restrict__ grad,
                  const float* __restrict__ partial_loss, float* __restrict__ loss, float* __restrict__ normpart,
                  float* __restrict__ params, float* __restrict__ m, float* __restrict__ v, int* __restrict__ step,
-                 float* __restrict__ wimg, unsigned long long* __restrict__ grid_bar,
+                 float* __restrict__ wimg, unsigned long long* __restrict__ nw,
                  const __grid_constant__ DpArgs a) {
   __shared__ __align__(16) float red[RED_PARTS][RED_IDX];
   __shared__ float wsum[RED_IDX / 32];
   __shared__ float lsum[RED_IDX / 32];
   __shared__ float s_norm;
-  __shared__ int s_ok;
+  __shared__ int s_ok, s_fail;
   const int i = threadIdx.x % RED_IDX, p = threadIdx.x / RED_IDX;
   const int idx = blockIdx.x * RED_IDX + i;
   auto tstamp = [&](int k) {
@@ -166,6 +154,15 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
   griddep_launch_dependents();     // the next step's flow kernel may start launching (it waits for this grid's end)
   griddep_wait();                  // the flow kernel's partial gradients and step counter are complete
   const int t = step[0];
+  // launch epoch of the norm words (nw[0] = launches so far, bumped by block 0 once it has seen every word)
+  const unsigned int lep = (unsigned int)__ldcg(nw) + 1u;
+  unsigned long long* const words = nw + 1;
+  auto publish = [&](float tt, bool ok) {
+    // {squared-norm partial, launch epoch | bit 31: this block gave up on a peer}: the value travels with its tag
+    const unsigned int tag = lep | (ok ? 0u : 0x80000000u);
+    const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(tt);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(words + blockIdx.x), "l"(w) : "memory");
+  };
   // DP: the locally reduced gradient is PUSHED into every rank's receive area of the coming epoch
   // (= count + 1; parity alternates): remote stores are fire-and-forget, the later sum reads local memory only
   const unsigned int epoch = (unsigned int)t + 1u;
@@ -202,7 +199,7 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
     if (!DP) {
       float tt = 0.f;
       for (int w = 0; w < RED_IDX / 32; ++w) tt += wsum[w];
-      normpart[blockIdx.x] = tt;
+      publish(tt, true);
     }
     if (blockIdx.x == 0) {
       float l = 0.f;
@@ -216,8 +213,8 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
       }
     }
     s_ok = 1;
+    s_fail = 0;
     tstamp(1);
-    if (!DP) grid_barrier(grid_bar, false);
   }
   tstamp(2);
   __syncthreads();
@@ -259,22 +256,49 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
     if (i == 0) {
       float tt = 0.f;
       for (int w = 0; w < RED_IDX / 32; ++w) tt += wsum[w];
-      normpart[blockIdx.x] = tt;
+      publish(tt, s_ok != 0);
       if (blockIdx.x == 0) loss[0] = s_ok ? l_tot : __int_as_float(0x7fc00000);
       tstamp(4);
-      grid_barrier(grid_bar, false);
-      tstamp(5);
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(RED_IDX));
   }
-  // A peer went missing (time-out above, in any block of this rank): every block sees the error word behind the
-  // grid barrier and the whole rank leaves params / m / v / step / the weight images untouched -- a stale word must
-  // never reach the optimiser state.  The loss is NaN and mafb200_dp_error reports it to the host.
-  const bool dp_fail = DP && __ldcg(a.error) != 0u;
-  if (dp_fail && blockIdx.x == 0 && i == 0) loss[0] = __int_as_float(0x7fc00000);
-  // every block sums the norm partials in the same fixed order -> identical scale everywhere
+  // what the update needs besides the norm: schedule, bias corrections, the parameter's slots in the weight images
+  const float lr_t = lr_schedule(O, t);
+  const float tn = (float)(t + 1);
+  const float d1 = 1.f - powf(O.b1, tn), d2 = 1.f - powf(O.b2, tn);
+  long long o1 = 0, o2 = -1;
+  if (idx < P.P) image_offsets(P, idx, o1, o2);
+  // Global norm without a grid barrier: every block polls every block's word (both of a thread's words requested
+  // together) and sums them in block order -> identical scale everywhere, one L2 round trip behind the last block.
+  // A peer went missing (time-out above, in any block of this rank): the block's tag says so, every block reads every
+  // tag, and the whole rank leaves params / m / v / step / the weight images untouched -- a stale word must never
+  // reach the optimiser state.  The loss is NaN and mafb200_dp_error reports it to the host.
   float ns = 0.f;
-  for (int q = i; q < (int)gridDim.x; q += RED_IDX) ns += __ldcg(normpart + q);
+  {
+    const long long tw = clock64();
+    const long long patience = DP ? a.timeout_cycles : 4000000000LL;
+    unsigned int bad = DP ? (__ldcg(a.error) != 0u ? 1u : 0u) : 0u;     // sticky: declared missing in an earlier step
+    auto ldw = [&](int q) {
+      unsigned long long w;
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(words + q) : "memory");
+      return w;
+    };
+    auto settle = [&](int q, unsigned long long w) -> float {
+      while (((unsigned int)(w >> 32) & 0x7fffffffu) != lep) {
+        if (clock64() - tw > patience) { w = 1ull << 63; break; }
+        w = ldw(q);
+      }
+      bad |= (unsigned int)(w >> 63);
+      return __uint_as_float((unsigned int)w);
+    };
+    const int nblk = (int)gridDim.x;
+    for (int q = i; q < nblk; q += 2 * RED_IDX) {
+      const bool two = q + RED_IDX < nblk;
+      const unsigned long long w0 = ldw(q), w1 = two ? ldw(q + RED_IDX) : 0ull;
+      ns += settle(q, w0);
+      if (two) ns += settle(q + RED_IDX, w1);
+    }
+    if (bad) atomicOr(&s_fail, 1);
+  }
   ns = warp_sum(ns);
   if ((i & 31) == 0) wsum[i >> 5] = ns;
   asm volatile("bar.sync 1, %0;" ::"n"(RED_IDX));
@@ -284,10 +308,15 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
     s_norm = sqrtf(tot);
   }
   asm volatile("bar.sync 1, %0;" ::"n"(RED_IDX));
+  tstamp(5);
+  const bool dp_fail = s_fail != 0;
+  if (dp_fail && blockIdx.x == 0 && i == 0) {
+    loss[0] = __int_as_float(0x7fc00000);
+    if (DP) *a.error = 1u;
+  }
   const float gnorm = s_norm;
   if (idx < P.P && !dp_fail) {
     if (!(gnorm < O.clip)) g = (g / gnorm) * O.clip;
-    const float lr_t = lr_schedule(O, t);
     float upd;
     if (O.kind == 1) {
       upd = g + O.weight_decay * pv;
@@ -296,17 +325,19 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
       const float v2 = O.b2 * vv + (1.f - O.b2) * g * g;
       m[idx] = mm;
       v[idx] = v2;
-      const float tn = (float)(t + 1);
-      const float mhat = mm / (1.f - powf(O.b1, tn));
-      const float vhat = v2 / (1.f - powf(O.b2, tn));
+      const float mhat = mm / d1;
+      const float vhat = v2 / d2;
       upd = mhat / (sqrtf(vhat) + O.eps);
       if (O.kind == 2) upd += O.weight_decay * pv;
     }
     pv = pv - lr_t * upd;
     params[idx] = pv;
-    write_image(P, wimg, idx, mk ? pv : 0.f);
+    const float iv = mk ? pv : 0.f;
+    wimg[o1] = iv;
+    if (o2 >= 0) wimg[o2] = iv;
   }
-  // every block read step[0] before the barrier
+  // block 0 has seen every block's word: every block has read step[0] and nw[0]
+  if (blockIdx.x == 0 && i == 0) *nw = (unsigned long long)lep;
   if (blockIdx.x == 0 && i == 0 && !dp_fail) step[0] = t + 1;
   tstamp(6);
 #ifdef MAFB_CTA_TIMES

@@ -67,7 +67,7 @@ struct mafb200_handle_s {
   float* normpart = nullptr;
   float* normsum = nullptr;     // [1] sum of the partials (large models: summed once, not by every block)
   unsigned int* done_counter = nullptr;
-  unsigned long long* grid_bar = nullptr;   // ticket counter of step_tail_kernel's grid barrier
+  unsigned long long* grid_bar = nullptr;   // step_tail_kernel: [0] launches so far, [1 + b] norm word of block b
   int tail_ok = -1;             // step_tail_kernel co-residency (-1: not probed yet)
   float logdet_const = 0.f;
   int n_norm = 0;
@@ -891,8 +891,8 @@ int mafb200_create(const MafDesc* desc, const int32_t* degrees, const float* shi
   CUH(cudaMalloc(&h->normsum, 4));
   CUH(cudaMalloc(&h->done_counter, 4));
   CUH(cudaMemset(h->done_counter, 0, 4));
-  CUH(cudaMalloc(&h->grid_bar, 8));
-  CUH(cudaMemset(h->grid_bar, 0, 8));
+  CUH(cudaMalloc(&h->grid_bar, (size_t)(h->n_norm + 2) * 8));
+  CUH(cudaMemset(h->grid_bar, 0, (size_t)(h->n_norm + 2) * 8));
 
   if (have_sampler) {
     // degree-sorted positions and group tables

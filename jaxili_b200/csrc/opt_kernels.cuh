@@ -49,21 +49,31 @@ __device__ __forceinline__ bool decode_param(const Plan& P, int idx, int& layer,
   return false;
 }
 
-__device__ __forceinline__ void write_image(const Plan& P, float* wimg, int idx, float masked_value) {
+// where parameter idx lives in the weight images (float offsets from the image base): o1 = forward image,
+// o2 = transposed (reverse-pass) image, -1 for a bias
+__device__ __forceinline__ void image_offsets(const Plan& P, int idx, long long& o1, long long& o2) {
   int layer, li, k, n;
   const bool is_bias = decode_param(P, idx, layer, li, k, n);
   const LinDesc& ln = P.lin[li];
-  float* base = wimg + (size_t)layer * P.img_floats;
+  const long long base = (long long)layer * P.img_floats;
   // forward image of the LAST linear: output columns interleaved (mu_j, logp_j) -> (2j, 2j+1), so that one
   // thread's 4-column tile holds both halves of a feature and the affine transform runs in the epilogue.
   // The transposed (reverse-pass) image keeps the parameter order.
   const int nf = (li == P.n_lin - 1) ? (n < P.D ? 2 * n : 2 * (n - P.D) + 1) : n;
   if (is_bias) {
-    base[ln.b_off + nf] = masked_value;
+    o1 = base + ln.b_off + nf;
+    o2 = -1;
   } else {
-    base[ln.w_off + k * ln.NP + nf] = masked_value;
-    base[P.fwd_floats + ln.wt_off + n * ln.KP + k] = masked_value;
+    o1 = base + ln.w_off + k * ln.NP + nf;
+    o2 = base + P.fwd_floats + ln.wt_off + n * ln.KP + k;
   }
+}
+
+__device__ __forceinline__ void write_image(const Plan& P, float* wimg, int idx, float masked_value) {
+  long long o1, o2;
+  image_offsets(P, idx, o1, o2);
+  wimg[o1] = masked_value;
+  if (o2 >= 0) wimg[o2] = masked_value;
 }
 
 __global__ void pack_kernel(const __grid_constant__ Plan P, const float* __restrict__ params,
