@@ -31,6 +31,9 @@ def build(force=False, verbose=False):
         cmd.insert(1, "-Xptxas=-v")
     if os.environ.get("MAFB_TRACE"):
         cmd.insert(1, "-DMAFB_TRACE")
+    for exp in os.environ.get("MAFB_EXP", "").split(","):
+        if exp:
+            cmd.insert(1, "-DMAFB_EXP_" + exp)
     if os.environ.get("MAFB_CTA_TIMES"):
         cmd.insert(1, "-DMAFB_CTA_TIMES")
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
