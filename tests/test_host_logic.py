@@ -408,7 +408,8 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
 def test_kernel_resource_budgets():
     """Regression guard on the built cubin (cuobjdump, no GPU): the fused flow kernels keep their accumulators in
     registers (one 512-thread CTA per SM: <= 128 registers, no local-memory stack) and the cooperative tail kernel
-    stays at 32 registers, which is what lets all ceil(P/128) blocks be co-resident two per SM."""
+    (256-thread blocks) stays within 128 registers, which is what lets all ceil(P/128) blocks be co-resident two per
+    SM; the chain kernel's training pass fits 480 threads (<= 128 registers) without spilling."""
     import shutil
     tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     if not os.path.isfile(tool):
@@ -427,7 +428,9 @@ def test_kernel_resource_budgets():
     for n, u in flow512.items():
         assert u["REG"] <= 128 and u["STACK"] == 0, (n, u)
     tails = {n: u for n, u in usage.items() if "step_tail_kernel" in n}
-    assert len(tails) == 2 and all(u["REG"] <= 32 for u in tails.values()), tails
+    assert len(tails) == 2 and all(u["REG"] <= 128 for u in tails.values()), tails
+    chains = {n: u for n, u in usage.items() if "maf_chain_kernelILb1E" in n}
+    assert len(chains) >= 4 and all(u["REG"] <= 128 for u in chains.values()), chains
     samplers = {n: u for n, u in usage.items() if "maf_sample_kernel" in n}
     assert samplers and all(u["STACK"] == 0 for u in samplers.values()), samplers
 
