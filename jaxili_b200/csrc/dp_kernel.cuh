@@ -155,7 +155,7 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
   griddep_wait();                  // the flow kernel's partial gradients and step counter are complete
   const int t = step[0];
   // launch epoch of the norm words (nw[0] = launches so far, bumped by block 0 once it has seen every word)
-  const unsigned int lep = (unsigned int)__ldcg(nw) + 1u;
+  const unsigned int lep = ((unsigned int)__ldcg(nw) + 1u) & 0x7fffffffu;   // 31 bits: bit 31 of a word's tag is the give-up flag
   unsigned long long* const words = nw + 1;
   auto publish = [&](float tt, bool ok) {
     // {squared-norm partial, launch epoch | bit 31: this block gave up on a peer}: the value travels with its tag
