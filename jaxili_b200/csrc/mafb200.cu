@@ -361,8 +361,9 @@ static size_t dp_total_floats(const Plan& P) { return dp_recv_off(P) + 2 * (2 * 
 // Programmatic dependent launch between the two kernels of a training step (and into the next step's flow kernel):
 // the dependent grid's CTAs are placed as the preceding grid's CTAs retire and run their independent prologue
 // (shared-memory initialisation; the tail's operand loads) under its drain.  Measured on B200 (c2, graph replay):
-// 57.32 us per step with, 57.37 us without -- the 185 KB flow CTA and the 1024-thread tail blocks cannot share an
-// SM, so nothing overlaps; kept behind MAFB200_PDL=1 (default off).
+// 57.32 us per step with, 57.37 us without -- the 185 KB / 61 k-register flow CTA and the tail blocks cannot share
+// an SM, and the flow CTAs still enter 3.8 us after the tail's last block has left (4.0 us without): nothing
+// overlaps; kept behind MAFB200_PDL=1 (default off).
 static bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("MAFB200_PDL"); return e && atoi(e) != 0; }();
   return on;
