@@ -10,7 +10,7 @@
 //     linear of every layer, forward and reverse; the two warps split the output columns of a product and meet
 //     at a 64-thread named barrier -- the only synchronisation on the dependent chain.  Two chain warps per
 //     sub-partition hide each other's latencies (tests/micro/lone_warp.cu: one warp alone runs the inner loop at
-//     51 cycles per 16 FFMA2, two reach the pipe's 37.5), issued with priority (highest warp ids).
+//     51 cycles per 16 FFMA2, two reach the pipe's 37.5); warp ids: producer, chain warps, gradient warps.
 //     A lane holds 8 rows x 4 columns and one of 4 parts of the reduction (32 accumulators, 3 loads per 16 packed
 //     FFMA2, operands prefetched through a register ring); a two-stage shuffle reduce-scatter leaves every lane
 //     2 columns x 2 rows per row block for the epilogue.
