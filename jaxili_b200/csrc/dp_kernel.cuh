@@ -21,6 +21,7 @@
 namespace mafb {
 
 constexpr int DP_MAX_WORLD = 8;
+constexpr long long kTailWaitCycles = 4000000000LL;   // ~2 s: the blocks of one cooperative launch waiting for each other
 
 struct DpArgs {
   int rank, world, P;
@@ -275,7 +276,7 @@ step_tail_kernel(const __grid_constant__ Plan P, const __grid_constant__ OptArgs
   float ns = 0.f;
   {
     const long long tw = clock64();
-    const long long patience = DP ? a.timeout_cycles : 4000000000LL;
+    const long long patience = DP ? a.timeout_cycles : kTailWaitCycles;
     unsigned int bad = DP ? (__ldcg(a.error) != 0u ? 1u : 0u) : 0u;     // sticky: declared missing in an earlier step
     auto ldw = [&](int q) {
       unsigned long long w;
