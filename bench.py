@@ -39,6 +39,18 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# Training steps captured per CUDA-graph launch of the resident-data loop (narrow workloads): the largest of these
+# that divides --steps, unless MAFB200_BENCH_GRAPH_STEPS says otherwise.  Measured on B200 (c2): 54.4 -> 52.5 us per
+# step at N=1, 66.0 -> 61.1 us at N=8 with 25 steps per launch -- the boundary between two graph launches costs
+# ~2 us more than a kernel-to-kernel edge inside a graph, and the ranks' launch jitter ends up in the exchange.
+SPL_CHOICES = (25, 20, 10, 8, 5, 4, 2, 1)
+
+
+def graph_steps(K):
+    e = os.environ.get("MAFB200_BENCH_GRAPH_STEPS")
+    if e:
+        return max(1, int(e))
+    return next(s for s in SPL_CHOICES if K % s == 0)
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
@@ -430,7 +442,7 @@ def run_workload(ctx, name, batch, K, W, full=True):
                               norm_current=world == 1)
             launches_per_step = 10 * (3 + 1 + 1 + 3 * 3 + 1) + 6
         elif world == 1:
-            step_fn = trainer.make_graph_step(theta_d, x_d, batch)
+            step_fn = trainer.make_graph_step(theta_d, x_d, batch, steps_per_launch=graph_steps(K))
             launches_per_step = 2          # flow kernel, cooperative tail (reduce + norm + clip + Adam + re-pack)
         else:
             state = trainer.state
@@ -447,7 +459,7 @@ def run_workload(ctx, name, batch, K, W, full=True):
             if peer:
                 # one-shot all-reduce over NVLink peer memory fused with the norm partials; no NCCL call
                 # is left in the step, so the whole step is one CUDA graph like the single-GPU case
-                step_fn = trainer.make_graph_step(theta_d, x_d, batch)
+                step_fn = trainer.make_graph_step(theta_d, x_d, batch, steps_per_launch=graph_steps(K))
             else:
                 def step_fn():
                     eng.loss_grad(flat, xd, yd, loss, grad, batch_rows=batch, inv_global_b=inv,
@@ -456,13 +468,15 @@ def run_workload(ctx, name, batch, K, W, full=True):
                     eng.clip_adam(flat, grad, state.opt_state["m"], state.opt_state["v"], state.step, state.tx)
             # peer: flow kernel + cooperative tail (reduce, exchange, clip, Adam); NCCL: flow, reduce, NCCL's, clip_adam
             launches_per_step = 2 if peer else 4
-        for _ in range(W):
+        spl = getattr(step_fn, "steps", 1)           # steps per call (one CUDA graph may hold several)
+        assert K % spl == 0, "--steps must be a multiple of the steps per graph launch"
+        for _ in range((W + spl - 1) // spl):
             step_fn()
         barrier_sync()
         clocks.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(K):
+        for _ in range(K // spl):
             step_fn()
         e1.record()
         barrier_sync()
@@ -585,6 +599,7 @@ def run_workload(ctx, name, batch, K, W, full=True):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(name, batch, world),
             "run": {"dataset_rows_per_gpu": rows, "l2": l2_note, "final_loss": final_loss,
+                    "steps_per_graph_launch": spl,
                     "allreduce": ("none" if world == 1 else ("nccl" if wide or not peer else "peer-memory one-shot (own kernel)"))},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": batch * (cfg["n_in"] + cfg["n_cond"]) * 4,
                     "d2h_bytes_per_step": 4, "steps": Ke if full is not None else 0,

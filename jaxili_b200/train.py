@@ -493,10 +493,11 @@ class TrainerModule:
 
         return train_step, eval_step
 
-    def make_graph_step(self, theta_dev, x_dev, batch_size):
+    def make_graph_step(self, theta_dev, x_dev, batch_size, steps_per_launch=1):
         """CUDA-graph replay of one whole step over a GPU-resident dataset: the batch is selected on
         the device from the optax step counter, so one graph launch = forward + backward + reduction
-        + clip + Adam with no host work.  Returns ``step() -> None`` (loss in ``self.last_loss``)."""
+        + clip + Adam with no host work.  Returns ``step() -> None`` (loss in ``self.last_loss``).
+        ``steps_per_launch`` > 1 captures that many consecutive steps in the one graph (``step.steps``)."""
         state = self.state
         eng = self.model.engine()
         _, world = parallel.world_info()
@@ -515,12 +516,16 @@ class TrainerModule:
 
         inv = 1.0 / (batch_size * world)
 
-        def body():
+        def one():
             # flow kernel + one cooperative tail kernel; with peers the one-shot exchange over NVLink peer
             # memory happens inside the tail (own kernel, graph-capturable -- unlike the NCCL call)
             eng.train_step(flat, xd, yd, loss, grad, state.opt_state["m"], state.opt_state["v"], state.step,
                            state.tx, batch_rows=batch_size, inv_global_b=inv, batch_index=state.step,
                            n_batches=n_batches, packed_current=True, dp_slot=peer)
+
+        def body():
+            for _ in range(max(1, int(steps_per_launch))):
+                one()
 
         s = torch.cuda.Stream(device=eng.device)
         s.wait_stream(torch.cuda.current_stream(eng.device))
@@ -534,6 +539,7 @@ class TrainerModule:
 
         def step():
             graph.replay()
+        step.steps = max(1, int(steps_per_launch))
         step.check = self._check_dp      # call at a host sync point: raises if a peer rank went missing
         return step
 

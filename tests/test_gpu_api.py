@@ -162,6 +162,20 @@ def test_graph_step_equals_eager_steps(tmp_path):
         i = s % 4
         b.state, _ = b.train_step(b.state, [theta[i * 512:(i + 1) * 512], x[i * 512:(i + 1) * 512]])
     assert torch.allclose(a.state.params.flat, b.state.params.flat, rtol=0, atol=1e-6)
+    # several steps per graph launch: same kernels in the same order -> bit-identical to one step per launch
+    c = mk()
+    step4 = c.make_graph_step(torch.tensor(theta, device="cuda:0"), torch.tensor(x, device="cuda:0"), 512,
+                              steps_per_launch=4)
+    assert step4.steps == 4
+    m0 = int(c.state.step.item())          # the warm-up run of the 4-step body
+    while int(c.state.step.item()) < n1:
+        step4()
+    d = mk()
+    step1 = d.make_graph_step(torch.tensor(theta, device="cuda:0"), torch.tensor(x, device="cuda:0"), 512)
+    while int(d.state.step.item()) < int(c.state.step.item()):
+        step1()
+    assert m0 == 4 and int(c.state.step.item()) == int(d.state.step.item())
+    assert torch.equal(c.state.params.flat, d.state.params.flat)
 
 
 def test_streamed_epoch_equals_plain_steps(tmp_path):
