@@ -491,7 +491,9 @@ def run_workload(ctx, name, batch, K, W, full=True):
             #     inputs are copied host->device inside the timed region (copy stream, overlapping the previous
             #     step) and every step's loss is copied device->host into a pinned ring right behind the step; the
             #     host reads the ring once per epoch, as the reference does (jaxili/train.py:446-449)
-            Ke = max(W, min(K, 10 if wide else 300))
+            # steady state: one epoch of at least 300 host batches for the narrow workloads (an epoch of 20 steps is
+            # dominated by its fill and drain: 66.6 vs 76 M samples/s at c2); the count is reported as e2e.steps
+            Ke = max(W, min(K, 10)) if wide else max(W, min(max(K, 300), 2000))
             n_host = min(n_batches, 16)
             host_batches = [[torch.from_numpy(np.ascontiguousarray(theta[i * batch:(i + 1) * batch])).pin_memory(),
                              torch.from_numpy(np.ascontiguousarray(x[i * batch:(i + 1) * batch])).pin_memory()]
