@@ -632,16 +632,24 @@ class TrainerModule:
 
     def _train_epoch_streamed(self, train_loader, num_train_steps, start_time):
         pipe, total, n = None, 0.0, 0
+        dev_total = None                             # losses of device-resident steps: summed on the device
         for batch in train_loader:
             first = batch[0]
             rows = first.shape[0]
             if isinstance(first, torch.Tensor) and first.is_cuda:
-                # device-resident batches need no staging: plain step
+                # device-resident batches need no staging: plain step; its loss word is added to a device scalar
+                # (stream-ordered, before the next step overwrites it) and read once at the end of the epoch,
+                # like the reference's single .item() (jaxili/train.py:446-449)
                 if pipe is not None:
                     total += float(pipe.drain().sum())
                     pipe = None                      # re-fenced behind the plain step when used again
                 self.state, m = self.train_step(self.state, batch)
-                total += float(m["loss"].item())
+                loss_t = m["loss"]
+                if isinstance(loss_t, torch.Tensor):
+                    loss_t = loss_t.reshape(-1)[:1].to(torch.float32)
+                    dev_total = loss_t.clone() if dev_total is None else dev_total.add_(loss_t)
+                else:
+                    total += float(loss_t)
                 n += 1
                 continue
             if pipe is None or pipe.rows != rows:
@@ -658,6 +666,8 @@ class TrainerModule:
             n += 1
         if pipe is not None:
             total += float(pipe.drain().sum())
+        if dev_total is not None:
+            total += float(dev_total.item())
         self._check_dp()
         return {"train/loss": total / max(num_train_steps, 1), "epoch_time": time.time() - start_time}
 
