@@ -496,3 +496,18 @@ def test_hmc_restatement_samples_the_right_distribution():
     assert s[:, 0].min() > -1 and s[:, 0].max() < 2
     assert abs(s[:, 0].mean() - m0) < 0.03 and abs(s[:, 0].var() - v0) < 0.03
     assert abs(s[:, 1].mean() - m1) < 0.02 and abs(s[:, 1].var() - v1) < 0.02
+
+
+def test_bench_graph_steps_divide_the_timed_steps(monkeypatch):
+    """bench.py times EXACTLY --steps steps: the number of steps captured per graph launch must divide it."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.delenv("MAFB200_BENCH_GRAPH_STEPS", raising=False)
+    for K in (1, 7, 20, 50, 64, 300, 5000, 4999):
+        s = bench.graph_steps(K)
+        assert 1 <= s <= 25 and K % s == 0, (K, s)
+    assert bench.graph_steps(20) == 20 and bench.graph_steps(5000) == 25 and bench.graph_steps(7) == 1
+    monkeypatch.setenv("MAFB200_BENCH_GRAPH_STEPS", "4")
+    assert bench.graph_steps(20) == 4
