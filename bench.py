@@ -572,7 +572,19 @@ def run_workload(ctx, name, batch, K, W, full=True):
                                   n_batches=n_batches, packed_current=True)
                 tot_ms, n_l = eng.flow_elapsed()
                 eng.flow_timing(False)
-                kernel_ms = tot_ms / max(n_l, 1)
+                kernel_ms_bracketed = tot_ms / max(n_l, 1)      # one event pair per launch (eager launches)
+                # the figure used: back-to-back launches of the flow kernel alone between ONE event pair, i.e. the
+                # kernel's launch period in steady state, as it runs inside the step's graph.  The per-launch event
+                # brackets above add their own stream operations around every kernel (52 vs ~47 us at c2).
+                torch.cuda.synchronize(dev)
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for i in range(Kr):
+                    eng.loss_grad(flat, xd, yd, loss, grad, batch_rows=batch, batch_index=trainer.state.step,
+                                  n_batches=n_batches, packed_current=True, flow_only=True)
+                f1.record()
+                torch.cuda.synchronize(dev)
+                kernel_ms = f0.elapsed_time(f1) / Kr
                 peak, peak_parts = fp32_peak_tflops(local)
                 achieved = flops_step / (kernel_ms * 1e-3) / 1e12
                 static = {}
@@ -585,7 +597,11 @@ def run_workload(ctx, name, batch, K, W, full=True):
                         "frac": achieved / peak, "traffic": static.get("dram_bytes_per_launch"),
                         "traffic_source": static.get("source", "not captured for this workload"),
                         "kernel": "maf_chain_kernel<BWD> (csrc/chain_kernel.cuh)",
-                        "kernel_us": kernel_ms * 1e3, "flops_per_launch": flops_step,
+                        "kernel_us": kernel_ms * 1e3, "kernel_us_event_bracketed": kernel_ms_bracketed * 1e3,
+                        "kernel_us_method": "back-to-back launches of the flow kernel alone between one CUDA event pair "
+                                            "(launch period, same batch every launch: the input is 0.3 MB of the 14 MB a launch moves); "
+                                            "kernel_us_event_bracketed: one event pair around every launch, walking through the dataset",
+                        "flops_per_launch": flops_step,
                         "flops_note": "dense reference-equivalent count 6*M*L per row (SURVEY 8d), masks not discounted; "
                                       "the kernel multiplies the masked zeros too (no tile skipping); it skips the input "
                                       "gradient of layer 0 and computes only the data columns of each layer's input gradient",

@@ -77,7 +77,11 @@ enum {
   /* loss_grad: write the reduced gradient and loss into this rank's symmetric (peer-mapped) slot
      instead of out_grad / out_loss; mafb200_dp_allreduce then sums the ranks' slots.
      train_step / pipeline_create: data-parallel step, the exchange runs inside the tail kernel. */
-  MAFB200_DP_SLOT = 4
+  MAFB200_DP_SLOT = 4,
+  /* loss_grad, measurement hook: launch the fused flow kernel only and leave out_loss / out_grad untouched
+     (the per-CTA partial gradients stay in the handle).  bench.py times back-to-back launches of it for the
+     roofline figure. */
+  MAFB200_FLOW_ONLY = 8
 };
 
 typedef struct mafb200_handle_s* mafb200_handle;

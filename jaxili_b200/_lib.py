@@ -23,6 +23,7 @@ ACTIVATIONS = {
 PACKED_CURRENT = 1
 NORM_CURRENT = 2
 DP_SLOT = 4
+FLOW_ONLY = 8
 
 
 class MafDesc(C.Structure):

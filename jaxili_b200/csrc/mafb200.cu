@@ -1386,6 +1386,7 @@ int mafb200_loss_grad(mafb200_handle h, const float* params, const float* x, con
   launch_flow<true>(h->flow_kernel, P, A, grid, st);
   CU(cudaGetLastError());
   if (h->timing) CU(cudaEventRecord(h->ev1, st));
+  if (flags & MAFB200_FLOW_ONLY) return 0;
   const size_t sf = dp_slot_floats(P);
   reduce_kernel<<<h->n_norm, RED_THREADS, 0, st>>>(h->partial, P.pgs, grid, P.P, h->mask, out_grad,
                                                          h->partial_loss, out_loss, h->normpart,

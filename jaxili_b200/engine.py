@@ -270,9 +270,10 @@ class MafEngine:
         return e.value
 
     def loss_grad(self, params, x, y, out_loss, out_grad, batch_rows=None, inv_global_b=None,
-                  batch_index=None, n_batches=1, packed_current=False, dp_slot=False):
+                  batch_index=None, n_batches=1, packed_current=False, dp_slot=False, flow_only=False):
         """out_loss[0], out_grad <- NLL and its gradient over rows [0, batch_rows) of x/y (or the
-        device-selected batch ``batch_index[0] % n_batches``)."""
+        device-selected batch ``batch_index[0] % n_batches``).  ``flow_only`` (measurement hook): only the fused
+        flow kernel is launched, out_loss / out_grad stay untouched."""
         px = self._chk(x, "x", self.n_in, align=4)     # misaligned row tiles take the kernels' element-wise staging path
         py = self._chk(y, "y", self.n_cond, align=4) if self.n_cond else None
         B = x.shape[0] if batch_rows is None else int(batch_rows)
@@ -286,7 +287,8 @@ class MafEngine:
         _lib.check(self.lib.mafb200_loss_grad(
             self._h, self._chk(params, "params"), px, py, B, inv, bi, int(n_batches),
             None if dp_slot else self._chk(out_loss, "out_loss"), None if dp_slot else self._chk(out_grad, "out_grad"),
-            (self._pc(params, packed_current)) | (_lib.DP_SLOT if dp_slot else 0), self._stream()))
+            (self._pc(params, packed_current)) | (_lib.DP_SLOT if dp_slot else 0) |
+            (_lib.FLOW_ONLY if flow_only else 0), self._stream()))
 
     @staticmethod
     def make_opt_desc(lr=1e-3, warmup=0.0, decay_steps=1e9, clip=5.0, b1=0.9, b2=0.999, eps=1e-8,
